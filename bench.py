@@ -1,0 +1,555 @@
+#!/usr/bin/env python
+"""bench.py -- detector scenes/s @40k points on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full detector forward (PointNet++ backbone SA1-4 + FP1-2, Hough voting, vote
+aggregation + proposal head + on-device box decode) over one batch of 8 synthetic 40k-point
+ScanNet-shaped scenes per GPU (BASELINE.json configs[1]; weak scaling: every rank has its own 8
+scenes, no data-path collective -- inference is embarrassingly parallel over scenes).
+
+  value   : scenes/s with the batch already resident in HBM (CUDA-event time, max over ranks)
+  e2e     : same, through the public module API from PINNED HOST buffers, host->device copy and
+            device->host read of the detections inside the timed region
+  roofline: the dominant roofline-bounded kernel of the step, timed live with CUDA events
+  cpu_baseline: the CPU oracle port (oracle/, C + torch CPU MLP) on a bounded sample (rank 0, N=1)
+  --impl reference: the reference's own CUDA ops (oracle/_ref, unmodified sources rebuilt for
+            sm_100a) in the reference's own op sequence, incl. its host-side box decode; falls
+            back to the CPU port when oracle/_ref is not loadable.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENES_PER_GPU = 8
+N_POINTS = 40000
+FEATURE_DIM = 1          # xyz + height: the reference's default "xyz" input
+CONFIG_ID = 2
+WORKLOAD = ("SpaCap3D xyz: batch 8 scenes x 40k pts per GPU, full detector forward "
+            "(SA 2048/1024/512/256, FP1-2, voting, 256 proposals, box decode)")
+N_INPUT_SETS = 3         # distinct batches rotated through the timed loop
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def make_host_batches(rank):
+    """N_INPUT_SETS pinned (8, 40000, 3+C) float32 batches; seeds differ per rank and per set."""
+    from spacap3d_b200.scenes import make_scene
+    sets = []
+    for s in range(N_INPUT_SETS):
+        scenes = [make_scene(1000 * CONFIG_ID + 100 * rank + 10 * s + i, N_POINTS, use_height=True)
+                  for i in range(SCENES_PER_GPU)]
+        t = torch.from_numpy(np.stack(scenes, 0))
+        sets.append(t.pin_memory() if torch.cuda.is_available() else t)
+    return sets
+
+
+def make_detector(device):
+    from spacap3d_b200.detector import VoteNetDetector
+    torch.manual_seed(0)
+    model = VoteNetDetector(input_feature_dim=FEATURE_DIM).to(device).eval()
+    return model
+
+
+RESULT_KEYS = ("objectness_scores", "center", "size_scores", "size_residuals", "sem_cls_scores",
+               "bbox_corner", "aggregated_vote_inds")
+
+
+class L2Flusher:
+    def __init__(self, device):
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel accounting: every call through the C ABI is timed with CUDA events on torch's current
+# stream (the stream the kernels are launched on)
+ALGO_BYTES = {
+    # SURVEY 8(d) per-scene formulas x B; args are the ctypes call arguments after the name
+    "spc_group_points": lambda a: 4 * a[2] * (a[3] * a[4] + a[5] * a[6] + a[3] * a[5] * a[6]),
+    "spc_group_points_grad": lambda a: 4 * a[2] * (a[3] * a[5] * a[6] + a[5] * a[6] + a[3] * a[4]),
+    "spc_three_interpolate": lambda a: 4 * a[3] * (a[4] * a[5] + 6 * a[6] + a[4] * a[6]),
+    "spc_three_interpolate_grad": lambda a: 4 * a[3] * (a[4] * a[5] + 6 * a[5] + a[4] * a[6]),
+    "spc_gather_points": lambda a: 4 * a[2] * (a[5] + 2 * a[3] * a[5]),
+    "spc_ball_query": lambda a: a[2] * (12 * a[3] + 12 * a[4] + 4 * a[4] * a[6]),
+    "spc_three_nn": lambda a: a[2] * (12 * (a[3] + a[4]) + 24 * a[3]),
+    "spc_furthest_point_sampling": lambda a: a[1] * (12 * a[2] + 4 * a[3] + (12 * a[3] if a[5] else 0)),
+}
+ROOFLINE_BOUNDED = ("spc_group_points", "spc_three_interpolate", "spc_gather_points", "spc_sa_fused_forward")
+
+
+class KernelMeter:
+    """Wraps spacap3d_b200._lib.call: counts launches, optionally records event pairs."""
+
+    def __init__(self):
+        from spacap3d_b200 import _lib
+        self._lib = _lib
+        self._orig = _lib.call
+        self.launches = 0
+        self.records = []      # (name, bytes, ev0, ev1, extra)
+        self.timing = False
+
+    def install(self):
+        def call(name, *args):
+            self.launches += 1
+            if not self.timing:
+                return self._orig(name, *args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._orig(name, *args)
+            e1.record()
+            fn = ALGO_BYTES.get(name)
+            self.records.append((name, fn(args) if fn else 0, e0, e1, args))
+        self._lib.call = call
+
+    def uninstall(self):
+        self._lib.call = self._orig
+
+    def summary(self, steps):
+        """per-op: launches/step, ms/step, algorithmic GB/s (aggregated over the step)."""
+        agg = {}
+        for name, nbytes, e0, e1, args in self.records:
+            ms = e0.elapsed_time(e1)
+            d = agg.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "max": (0.0, 0, None)})
+            d["launches"] += 1
+            d["ms"] += ms
+            d["bytes"] += nbytes
+            if ms > d["max"][0]:
+                d["max"] = (ms, nbytes, args)
+        return agg
+
+
+# ------------------------------------------------------------------------------------------------
+def forward_resident(model, pc):
+    with torch.no_grad():
+        return model({"point_clouds": pc})
+
+
+def timed_loop(step_fn, steps, warmup, flush, barrier, sampler=None):
+    """W warm-up steps, then exactly K timed steps; each step is bracketed by CUDA events on the
+    launching stream with an L2 flush in between (outside the events).  Returns per-step ms."""
+    for i in range(warmup):
+        flush()
+        step_fn(i)
+    torch.cuda.synchronize()
+    barrier()
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0 = time.perf_counter()
+    for k in range(steps):
+        flush()
+        ev[k][0].record()
+        step_fn(warmup + k)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    return [a.elapsed_time(b) for a, b in ev], wall, clocks
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        barrier = lambda: dist.barrier(device_ids=[local])
+    else:
+        dist = None
+        barrier = lambda: None
+    from spacap3d_b200 import _lib
+    _lib.load()
+    meter = KernelMeter()
+    meter.install()
+    model = make_detector(device)
+    host = make_host_batches(rank)
+    resident = [h.to(device) for h in host]
+    flush = L2Flusher(device)
+
+    # ---- (1) value: inputs resident in HBM ------------------------------------------------------
+    out_holder = {}
+
+    def step_resident(i):
+        out_holder["o"] = forward_resident(model, resident[i % N_INPUT_SETS])
+
+    meter.launches = 0
+    per_step, wall, clocks = timed_loop(step_resident, args.steps, args.warmup, flush, barrier,
+                                        ClockSampler(local))
+    launches_per_step = meter.launches // (args.steps + args.warmup)
+    dev_s = sum(per_step) / 1e3
+
+    # ---- (2) e2e: pinned host -> device -> forward -> device -> host ---------------------------
+    d2h_bytes = [0]
+
+    def step_e2e(i):
+        pc = host[i % N_INPUT_SETS].to(device, non_blocking=True)
+        o = forward_resident(model, pc)
+        res = [o[k].to("cpu", non_blocking=False) for k in RESULT_KEYS]
+        d2h_bytes[0] = sum(r.numel() * r.element_size() for r in res)
+
+    e2e_steps, e2e_wall, _ = timed_loop(step_e2e, args.steps, args.warmup, flush, barrier)
+    e2e_s = sum(e2e_steps) / 1e3
+    h2d_bytes = host[0].numel() * host[0].element_size()
+
+    # ---- (3) per-kernel event timing (separate pass so the events do not perturb (1)) ----------
+    prof_steps = min(args.steps, 5)
+    meter.timing = True
+    for i in range(prof_steps):
+        flush()
+        step_resident(i)
+    torch.cuda.synchronize()
+    meter.timing = False
+    agg = meter.summary(prof_steps)
+    meter.uninstall()
+
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([dev_s, e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+    total_scenes = SCENES_PER_GPU * world * args.steps
+    hbm_peak, tf_peak, peak_src = peaks()
+
+    ops = {}
+    step_ms_kernels = 0.0
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        ms = d["ms"] / prof_steps
+        step_ms_kernels += ms
+        ops[name.replace("spc_", "")] = {
+            "launches_per_step": d["launches"] // prof_steps, "ms_per_step": round(ms, 4),
+            "algo_gbs": round(d["bytes"] / prof_steps / (ms * 1e-3) / 1e9, 1) if ms > 0 else None}
+    dom = None
+    for name, d in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+        if name in ROOFLINE_BOUNDED:
+            dom = (name, d)
+            break
+    roofline = None
+    if dom is not None:
+        name, d = dom
+        avg_ms = d["ms"] / d["launches"]
+        avg_bytes = d["bytes"] / d["launches"]
+        achieved = avg_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": name.replace("spc_", ""), "bound": "hbm", "achieved": round(achieved, 1),
+                    "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
+                    "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": d["launches"] // prof_steps,
+                    "avg_launch_us": round(avg_ms * 1e3, 2), "algo_bytes_per_launch": int(avg_bytes),
+                    "share_of_step": round(d["ms"] / prof_steps / (dev_s / args.steps * 1e3), 4)}
+    fps = agg.get("spc_furthest_point_sampling")
+    latency_bound = None
+    if fps:
+        rounds = sum(max(r[4][3] - 1, 0) for r in meter.records if r[0] == "spc_furthest_point_sampling")
+        latency_bound = {"kernel": "furthest_point_sampling", "ms_per_step": round(fps["ms"] / prof_steps, 4),
+                         "us_per_round": round(fps["ms"] * 1e3 / max(rounds, 1), 4),
+                         "sequential_rounds_per_step": rounds // prof_steps}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline(model)
+
+    if rank == 0:
+        line = {
+            "metric": "detector scenes/s @40k pts", "value": round(total_scenes / dev_s, 3),
+            "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dev_s / args.steps * 1e3, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+                       "input_feature_dim": FEATURE_DIM, "weights": "random init (seed 0), eval mode",
+                       "l2": "256 MiB L2 flush between timed steps; %d rotating input batches" % N_INPUT_SETS,
+                       "parallelism": "scenes sharded by batch, %d rank(s), no collective" % world},
+            "e2e": {"value": round(total_scenes / e2e_s, 3), "unit": "scenes/s",
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes[0]),
+                    "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "roofline": roofline, "latency_bound": latency_bound, "ops": ops,
+            "kernel_ms_per_step": round(step_ms_kernels, 4),
+            "cpu_baseline": cpu_base, "clocks": clocks,
+            "wall_s_timed_region": round(wall, 4),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-structured pipeline on an arbitrary op provider (reference CUDA ext or the CPU oracle)
+class OracleOps:
+    """The nine `_ext` entry points on CPU torch tensors, backed by the C oracle (port)."""
+
+    def __init__(self):
+        import oracle
+        self.o = oracle
+
+    @staticmethod
+    def _t(a):
+        return torch.from_numpy(a)
+
+    def furthest_point_sampling(self, p, n):
+        return self._t(self.o.furthest_point_sampling(p.numpy(), n))
+
+    def gather_points(self, p, i):
+        return self._t(self.o.gather_points(p.numpy(), i.numpy()))
+
+    def ball_query(self, q, p, r, ns):
+        return self._t(self.o.ball_query(q.numpy(), p.numpy(), r, ns))
+
+    def group_points(self, p, i):
+        return self._t(self.o.group_points(p.numpy(), i.numpy()))
+
+    def three_nn(self, u, k):
+        d, i = self.o.three_nn(u.numpy(), k.numpy())
+        return [self._t(d), self._t(i)]
+
+    def three_interpolate(self, p, i, w):
+        return self._t(self.o.three_interpolate(p.numpy(), i.numpy(), w.numpy()))
+
+
+class swapped_ops:
+    """Route pointnet2_utils / pointnet2_modules to another op provider and force the
+    reference's unfused op sequence (FPS -> gather -> ball query -> 2x grouping -> cat -> MLP)."""
+
+    def __init__(self, provider, host_decode):
+        self.provider, self.host_decode = provider, host_decode
+
+    def __enter__(self):
+        from spacap3d_b200 import detector, pointnet2_modules, pointnet2_utils
+        self.mods = (pointnet2_utils, pointnet2_modules)
+        self.saved = [(m, m._ext) for m in self.mods]
+        for m in self.mods:
+            m._ext = self.provider
+        self.saved_fast = pointnet2_modules.FAST_PATHS
+        pointnet2_modules.FAST_PATHS = False
+        self.saved_decode = detector.ProposalModule.decode_pred_box
+        if self.host_decode:
+            detector.ProposalModule.decode_pred_box = reference_host_decode
+        return self
+
+    def __exit__(self, *exc):
+        from spacap3d_b200 import detector, pointnet2_modules
+        for m, e in self.saved:
+            m._ext = e
+        pointnet2_modules.FAST_PATHS = self.saved_fast
+        detector.ProposalModule.decode_pred_box = self.saved_decode
+
+
+def reference_host_decode(self, data_dict):
+    """The reference's decode_pred_box (models/proposal_module.py:81-104): device->host, numpy,
+    Python loop over the batch, host->device.  Used by the reference arm only."""
+    center = data_dict["center"].detach().cpu().numpy()
+    size_class = torch.argmax(data_dict["size_scores"], -1)
+    residual = torch.gather(data_dict["size_residuals"], 2,
+                            size_class.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, 1, 3))
+    size_class = size_class.detach().cpu().numpy()
+    residual = residual.squeeze(2).detach().cpu().numpy()
+    signs = np.array([[1, 1, 1], [1, -1, 1], [-1, -1, 1], [-1, 1, 1],
+                      [1, 1, -1], [1, -1, -1], [-1, -1, -1], [-1, 1, -1]], np.float64)
+    boxes = []
+    for i in range(center.shape[0]):
+        size = self.mean_size_arr[size_class[i]] + residual[i]
+        corners = signs[None] * (size / 2)[:, None, :] + center[i][:, None, :].astype(np.float64)
+        boxes.append(torch.from_numpy(corners).to(data_dict["center"].device).unsqueeze(0))
+    return torch.cat(boxes, 0)
+
+
+def cpu_baseline(model_gpu, budget_s=20.0):
+    """BASELINE.json configs[0]: one 40k-point scene, batch 1, full detector forward with the CPU
+    oracle ops (C port of the reference kernels, OpenMP) + torch CPU MLPs, on the host cores."""
+    import copy
+    from spacap3d_b200.scenes import make_scene
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = copy.deepcopy(model_gpu).to("cpu").eval()
+    scenes = [torch.from_numpy(make_scene(1000 + i, N_POINTS, use_height=True)[None]) for i in range(2)]
+    n, t0 = 0, time.perf_counter()
+    with swapped_ops(OracleOps(), host_decode=False), torch.no_grad():
+        model({"point_clouds": scenes[0]})          # warm-up (page-in, thread pools)
+        t0 = time.perf_counter()
+        while True:
+            model({"point_clouds": scenes[n % 2]})
+            n += 1
+            el = time.perf_counter() - t0
+            if el > budget_s or n >= 12:
+                break
+    return {"value": round(n / el, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": "%d forward(s) of one 40k-pt scene, batch 1 (configs[0]), %.1f s; oracle C ops "
+                      "(OpenMP) + torch CPU MLP" % (n, el)}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    ref = None
+    why = ""
+    if torch.cuda.is_available():
+        try:
+            from oracle.build_ref import load_ref
+            ref = load_ref()
+        except Exception as e:  # noqa: BLE001
+            why = "oracle/_ref not loadable (%s); CPU port used" % type(e).__name__
+    else:
+        why = "no GPU; CPU port used"
+    config = {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
+              "input_feature_dim": FEATURE_DIM, "weights": "random init (seed 0), eval mode"}
+    if ref is not None:
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        model = make_detector(device)
+        host = make_host_batches(rank)
+        resident = [h.to(device) for h in host]
+        flush = L2Flusher(device)
+        with swapped_ops(ref, host_decode=True):
+            def step(i):
+                forward_resident(model, resident[i % N_INPUT_SETS])
+            per_step, wall, clocks = timed_loop(step, args.steps, args.warmup, flush, lambda: None,
+                                                ClockSampler(local))
+        s = sum(per_step) / 1e3
+        val = SCENES_PER_GPU * args.steps / s
+        config["l2"] = "256 MiB L2 flush between timed steps"
+        config["arm"] = ("reference CUDA ops (lib/pointnet2/_ext_src rebuilt unmodified for sm_100a) in the "
+                         "reference op sequence + cuDNN MLP (torch defaults, TF32 conv) + host box decode; 1 GPU")
+        line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 3),
+                "unit": "scenes/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(s / args.steps * 1e3, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "device": "cuda",
+                "cpu_baseline": {"value": round(val, 3), "unit": "scenes/s", "cores": 0, "kind": "reference",
+                                 "sample": "%d steps x 8 scenes on the GPU (the reference has no CPU path: "
+                                           "'CPU not supported', sampling.cpp:33-35)" % args.steps},
+                "e2e": {"value": round(val, 3), "unit": "scenes/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "clocks": clocks}
+        print(json.dumps(line))
+        return
+    # CPU port: bounded sample = `steps` single-scene forwards
+    model = make_detector("cpu")
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from spacap3d_b200.scenes import make_scene
+    scene = torch.from_numpy(make_scene(1000, N_POINTS, use_height=True)[None])
+    steps = max(1, min(args.steps, 5))
+    with swapped_ops(OracleOps(), host_decode=True), torch.no_grad():
+        for _ in range(min(args.warmup, 1)):
+            model({"point_clouds": scene})
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            model({"point_clouds": scene})
+        el = time.perf_counter() - t0
+    val = steps / el
+    config["arm"] = "CPU oracle port, batch 1 per step; " + why
+    line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 4),
+            "unit": "scenes/s", "n_gpus": 1, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": round(el / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "device": "cpu",
+            "cpu_baseline": {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
+                             "sample": "%d single-scene forwards" % steps},
+            "e2e": {"value": round(val, 4), "unit": "scenes/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,92 @@
+/*
+ * spacap3d_ops.h -- C ABI of libspacap3d_ops.so: B200 (sm_100a) kernels for the PointNet++ /
+ * VoteNet point-set operators that SpaCap3D's detector runs on.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the reference's
+ * pybind11 module `pointnet2._ext` (lib/pointnet2/_ext_src/src/bindings.cpp:6-19); the
+ * reference-side file:line it stands in for is cited per function.  Differences by design:
+ *   - plain pointers + sizes, no torch types; the CALLER allocates every output and workspace;
+ *   - the stream is explicit (the reference uses at::cuda::getCurrentCUDAStream());
+ *   - a failed launch returns a non-zero status and sets spc_last_error(); it never calls
+ *     exit(-1) (reference: include/cuda_utils.h:30-39);
+ *   - outputs need NOT be zero-initialised by the caller: every element is written
+ *     (the reference relies on torch::zeros, e.g. ball_query.cpp:19-21).
+ * All pointers are DEVICE pointers on the current device.  float = IEEE fp32, indices = int32.
+ * All tensors are dense, row-major ("contiguous") in the layouts given below.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Thread-safety: no mutable global state except a thread-local error string.
+ */
+#ifndef SPACAP3D_OPS_H
+#define SPACAP3D_OPS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPC_OK 0
+#define SPC_ERR_INVALID_ARG 1
+#define SPC_ERR_CUDA 2
+#define SPC_ERR_UNSUPPORTED 3
+
+/* ABI version of this header (bumped on any signature change). */
+int spc_abi_version(void);
+/* Thread-local, NUL-terminated description of the last non-zero status on this thread. */
+const char *spc_last_error(void);
+
+/* furthest_point_sampling(points, nsamples)              sampling.cpp:66-87, sampling_gpu.cu:69-229
+ * xyz (B,N,3) -> idx (B,npoint).  Bit-exact with the reference including its tie-breaking
+ * (bit-reversed thread id of a 512-thread tree) and its |p|^2 <= 1e-3 skip.
+ * new_xyz (B,npoint,3) is optional (may be NULL): the sampled coordinates, i.e. the fused
+ * gather_points that always follows FPS in the SA modules (pointnet2_modules.py:237-242).
+ * No global workspace: running min-distances live in registers / distributed shared memory. */
+int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint, int32_t *idx,
+                                float *new_xyz, void *stream);
+
+/* gather_points(points, idx)                             sampling.cpp:15-38, sampling_gpu.cu:8-30
+ * points (B,C,N), idx (B,M) -> out (B,C,M) */
+int spc_gather_points(const float *points, const int32_t *idx, int B, int C, int N, int M,
+                      float *out, void *stream);
+
+/* gather_points_grad(grad_out, idx, n)                   sampling.cpp:40-65, sampling_gpu.cu:34-57
+ * grad_out (B,C,M), idx (B,M) -> grad_points (B,C,N) (zeroed here, then scatter-added) */
+int spc_gather_points_grad(const float *grad_out, const int32_t *idx, int B, int C, int N, int M,
+                           float *grad_points, void *stream);
+
+/* ball_query(new_xyz, xyz, radius, nsample)              ball_query.cpp:8-32, ball_query_gpu.cu:9-54
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample): first nsample indices (ascending) with
+ * d2 < radius*radius, padded with the first hit; all zeros when the ball is empty. */
+int spc_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                   int nsample, int32_t *idx, void *stream);
+
+/* group_points(points, idx)                              group_points.cpp:12-36, group_points_gpu.cu:8-39
+ * points (B,C,N), idx (B,npoint,nsample) -> out (B,C,npoint,nsample) */
+int spc_group_points(const float *points, const int32_t *idx, int B, int C, int N, int npoint,
+                     int nsample, float *out, void *stream);
+
+/* group_points_grad(grad_out, idx, n)                    group_points.cpp:38-62, group_points_gpu.cu:43-75
+ * grad_out (B,C,npoint,nsample), idx (B,npoint,nsample) -> grad_points (B,C,N) */
+int spc_group_points_grad(const float *grad_out, const int32_t *idx, int B, int C, int N,
+                          int npoint, int nsample, float *grad_points, void *stream);
+
+/* three_nn(unknowns, knows)                              interpolate.cpp:14-40, interpolate_gpu.cu:9-68
+ * unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) SQUARED distances ascending, idx (B,n,3).
+ * m < 3 leaves +inf / index 0 in the unfilled slots, like the reference. */
+int spc_three_nn(const float *unknown, const float *known, int B, int n, int m, float *dist2,
+                 int32_t *idx, void *stream);
+
+/* three_interpolate(points, idx, weight)                 interpolate.cpp:42-70, interpolate_gpu.cu:72-111
+ * points (B,C,m), idx (B,n,3), weight (B,n,3) -> out (B,C,n) */
+int spc_three_interpolate(const float *points, const int32_t *idx, const float *weight, int B,
+                          int C, int m, int n, float *out, void *stream);
+
+/* three_interpolate_grad(grad_out, idx, weight, m)       interpolate.cpp:71-99, interpolate_gpu.cu:116-154
+ * grad_out (B,C,n), idx (B,n,3), weight (B,n,3) -> grad_points (B,C,m) */
+int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const float *weight,
+                               int B, int C, int n, int m, float *grad_points, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPACAP3D_OPS_H */

@@ -1,0 +1,169 @@
+"""Drop-in for the reference's pybind11 module `pointnet2._ext`
+(lib/pointnet2/_ext_src/src/bindings.cpp:6-19): the same nine callables with the same argument
+order, dtype/contiguity/device checks (include/utils.h:5-25 -> RuntimeError) and return values,
+implemented by libspacap3d_ops.so through its C ABI (include/spacap3d_ops.h).
+
+Differences, all invisible to callers: outputs are allocated with torch.empty (every element is
+written by the kernels), launches go to torch's *current* stream under a device guard taken from
+the input tensor, and a failed launch raises instead of calling exit(-1).
+"""
+import torch
+
+from . import _lib
+
+
+def _check(t, name, dtype):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError("%s must be a tensor" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous tensor" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s tensor" % (name, "a float" if dtype == torch.float32 else "an int"))
+    if not t.is_cuda:
+        raise RuntimeError("CPU not supported")  # sampling.cpp:33-35 etc.
+
+
+def _same_device(a, *rest):
+    for t in rest:
+        if t.device != a.device:
+            raise RuntimeError("all tensors must be on the same CUDA device")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def furthest_point_sampling(points, nsamples):
+    """(B,N,3) f32 -> (B,nsamples) i32.   sampling.cpp:66-87"""
+    _check(points, "points", torch.float32)
+    B, N, _ = points.shape
+    out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
+                  out.data_ptr(), None, _stream())
+    return out
+
+
+def furthest_point_sampling_with_xyz(points, nsamples):
+    """Extension: FPS that also returns the sampled coordinates (B,nsamples,3) from the same
+    kernel (the gather that always follows FPS, pointnet2_modules.py:237-242)."""
+    _check(points, "points", torch.float32)
+    B, N, _ = points.shape
+    out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
+    new_xyz = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
+                  out.data_ptr(), new_xyz.data_ptr(), _stream())
+    return out, new_xyz
+
+
+def gather_points(points, idx):
+    """(B,C,N), (B,M) -> (B,C,M).   sampling.cpp:15-38"""
+    _check(points, "points", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _same_device(points, idx)
+    B, C, N = points.shape
+    M = idx.shape[1]
+    out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_gather_points", points.data_ptr(), idx.data_ptr(), B, C, N, M,
+                  out.data_ptr(), _stream())
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    """(B,C,M), (B,M) -> (B,C,n).   sampling.cpp:40-65"""
+    _check(grad_out, "grad_out", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _same_device(grad_out, idx)
+    B, C, M = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("spc_gather_points_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(n), M,
+                  out.data_ptr(), _stream())
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """(B,M,3), (B,N,3) -> (B,M,nsample) i32.   ball_query.cpp:8-32"""
+    _check(new_xyz, "new_xyz", torch.float32)
+    _check(xyz, "xyz", torch.float32)
+    _same_device(new_xyz, xyz)
+    B, M, _ = new_xyz.shape
+    N = xyz.shape[1]
+    out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    with torch.cuda.device(new_xyz.device):
+        _lib.call("spc_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius),
+                  int(nsample), out.data_ptr(), _stream())
+    return out
+
+
+def group_points(points, idx):
+    """(B,C,N), (B,npoint,nsample) -> (B,C,npoint,nsample).   group_points.cpp:12-36"""
+    _check(points, "points", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _same_device(points, idx)
+    B, C, N = points.shape
+    _, npoint, nsample = idx.shape
+    out = torch.empty((B, C, npoint, nsample), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_group_points", points.data_ptr(), idx.data_ptr(), B, C, N, npoint, nsample,
+                  out.data_ptr(), _stream())
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """(B,C,npoint,nsample), (B,npoint,nsample) -> (B,C,n).   group_points.cpp:38-62"""
+    _check(grad_out, "grad_out", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _same_device(grad_out, idx)
+    B, C, npoint, nsample = grad_out.shape
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("spc_group_points_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(n),
+                  npoint, nsample, out.data_ptr(), _stream())
+    return out
+
+
+def three_nn(unknowns, knows):
+    """(B,n,3), (B,m,3) -> [dist2 (B,n,3) f32, idx (B,n,3) i32].   interpolate.cpp:14-40"""
+    _check(unknowns, "unknowns", torch.float32)
+    _check(knows, "knows", torch.float32)
+    _same_device(unknowns, knows)
+    B, n, _ = unknowns.shape
+    m = knows.shape[1]
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    with torch.cuda.device(unknowns.device):
+        _lib.call("spc_three_nn", unknowns.data_ptr(), knows.data_ptr(), B, n, m,
+                  dist2.data_ptr(), idx.data_ptr(), _stream())
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    """(B,C,m), (B,n,3), (B,n,3) -> (B,C,n).   interpolate.cpp:42-70"""
+    _check(points, "points", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _check(weight, "weight", torch.float32)
+    _same_device(points, idx, weight)
+    B, C, m = points.shape
+    n = idx.shape[1]
+    out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_three_interpolate", points.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+                  B, C, m, n, out.data_ptr(), _stream())
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """(B,C,n), (B,n,3), (B,n,3) -> (B,C,m).   interpolate.cpp:71-99"""
+    _check(grad_out, "grad_out", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _check(weight, "weight", torch.float32)
+    _same_device(grad_out, idx, weight)
+    B, C, n = grad_out.shape
+    out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.call("spc_three_interpolate_grad", grad_out.data_ptr(), idx.data_ptr(),
+                  weight.data_ptr(), B, C, n, int(m), out.data_ptr(), _stream())
+    return out

@@ -1,0 +1,65 @@
+"""ctypes binding of libspacap3d_ops.so (include/spacap3d_ops.h).
+
+There is deliberately NO fallback: if the CUDA library is missing or a call fails, an exception
+is raised.  Nothing here imports the test oracle.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspacap3d_ops.so")
+ABI_VERSION = 1
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+
+# name -> argtypes, exactly the prototypes of include/spacap3d_ops.h
+SIGNATURES = {
+    "spc_furthest_point_sampling": [_p, _i, _i, _i, _p, _p, _p],
+    "spc_gather_points": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "spc_gather_points_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "spc_ball_query": [_p, _p, _i, _i, _i, _f, _i, _p, _p],
+    "spc_group_points": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "spc_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "spc_three_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "spc_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+}
+
+_lib = None
+
+
+class SpcError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library (once).  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpcError(
+            "libspacap3d_ops.so is not built (%s).  Run `python -m spacap3d_b200.build` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.spc_abi_version.restype = _i
+    lib.spc_last_error.restype = ctypes.c_char_p
+    if lib.spc_abi_version() != ABI_VERSION:
+        raise SpcError("libspacap3d_ops.so ABI %d != expected %d; rebuild" %
+                       (lib.spc_abi_version(), ABI_VERSION))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _i
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    status = getattr(lib, name)(*args)
+    if status != 0:
+        raise SpcError("%s failed (status %d): %s" %
+                       (name, status, lib.spc_last_error().decode("utf-8", "replace")))

@@ -1,0 +1,279 @@
+// fps.cu -- furthest point sampling as a thread-block-cluster kernel (sm_100a).
+//
+// Replaces furthest_point_sampling_kernel (reference sampling_gpu.cu:69-229), which runs ONE
+// 512-thread block per scene and read-modify-writes a global `temp` array every round.
+//
+// Design (B200-first):
+//  * one CLUSTER of C CTAs per scene (C = 1..16); every point's xyz and running min-distance
+//    stay in REGISTERS for the whole kernel (P points per thread) -- no global traffic at all
+//    inside the npoint-1 sequential rounds;
+//  * per round: P fused distance/min updates per thread, a 2-instruction warp arg-max
+//    (redux.sync max on the distance bits, redux.sync min on the tie-break key), one
+//    __syncthreads for the CTA-level candidate table, then every CTA pushes its candidate
+//    (distance, key, x, y, z) into every peer's shared memory through DSMEM and one
+//    cluster barrier publishes it -- each CTA then reduces the C candidates redundantly, so
+//    the winner's coordinates are already on-chip for the next round;
+//  * bit-exactness with the reference's block-tree arg-max: among equal maxima the reference
+//    keeps the candidate with the smallest (bit-reversed thread id, k div T), T =
+//    opt_n_threads(N).  Points are assigned to threads in exactly that order
+//    ("virtual index" v = bitrev(k mod T) * Q + k div T, Q = ceil(N/T)), so "max distance, then
+//    min v" reproduces the tree, and each thread's strict '>' scan reproduces the per-thread rule;
+//  * the |p|^2 <= 1e-3 skip (sampling_gpu.cu:100-101, compared in double) is evaluated once at
+//    load time: skipped / out-of-range slots get min-distance -1 and can never win.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace spc {
+
+constexpr int kMaxCluster = 16;
+
+struct FpsParams {
+  const float *xyz;   // (B,N,3)
+  int32_t *idx;       // (B,npoint)
+  float *new_xyz;     // (B,npoint,3) or nullptr
+  int N, npoint;
+  int T, log2T, Q;    // reference thread count, its log2, ceil(N/T)
+};
+
+__device__ __forceinline__ int fps_v_to_k(unsigned v, int Q, int T, int log2T) {
+  const unsigned r = v / (unsigned)Q;
+  const unsigned q = v - r * (unsigned)Q;
+  const unsigned res = log2T ? (__brev(r) >> (32 - log2T)) : 0u;
+  return (int)(q * (unsigned)T + res);
+}
+
+// XYZ_REGS: coordinates in registers (fast path); otherwise they are read from shared memory
+// every round (large-N fallback, P up to 32 with 512 threads).
+template <int P, int THREADS, bool XYZ_REGS>
+__global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams p) {
+  constexpr int NW = THREADS / 32;
+  extern __shared__ float s_xyz[];  // [3][P][THREADS] SoA copy of this CTA's points
+  float *sx = s_xyz, *sy = s_xyz + P * THREADS, *sz = s_xyz + 2 * P * THREADS;
+  __shared__ unsigned w_key[2][NW], w_v[2][NW];
+  __shared__ float w_x[2][NW], w_y[2][NW], w_z[2][NW];
+  __shared__ unsigned c_key[2][kMaxCluster], c_v[2][kMaxCluster];
+  __shared__ float c_x[2][kMaxCluster], c_y[2][kMaxCluster], c_z[2][kMaxCluster];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
+  const int scene = blockIdx.y;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u, warp = tid >> 5;
+  const float *xyz = p.xyz + (size_t)scene * p.N * 3;
+  const unsigned g = rank * THREADS + tid;      // thread id within the cluster
+  const unsigned v0 = g * P;                    // first virtual index owned by this thread
+  const unsigned V = (unsigned)p.T * (unsigned)p.Q;
+
+  float x[P], y[P], z[P], t[P];
+#pragma unroll
+  for (int s = 0; s < P; ++s) {
+    const unsigned v = v0 + s;
+    float px = 0.f, py = 0.f, pz = 0.f, pt = -1.0f;
+    if (v < V) {
+      const int k = fps_v_to_k(v, p.Q, p.T, p.log2T);
+      if (k < p.N) {
+        px = __ldg(xyz + 3 * k + 0);
+        py = __ldg(xyz + 3 * k + 1);
+        pz = __ldg(xyz + 3 * k + 2);
+        const float mag = __fmaf_rn(pz, pz, __fmaf_rn(px, px, __fmul_rn(py, py)));
+        pt = ((double)mag <= 1e-3) ? -1.0f : 1e10f;   // reference compares in double (F5)
+      }
+    }
+    sx[s * THREADS + tid] = px;
+    sy[s * THREADS + tid] = py;
+    sz[s * THREADS + tid] = pz;
+    if (XYZ_REGS) { x[s] = px; y[s] = py; z[s] = pz; }
+    t[s] = pt;
+  }
+  // point 0 is always the first pick (sampling_gpu.cu:85-86) and the fallback when no valid
+  // point exists (every thread reports best=-1, besti=0 => dists_i[0] == 0).
+  const float p0x = p.N > 0 ? __ldg(xyz + 0) : 0.f, p0y = p.N > 0 ? __ldg(xyz + 1) : 0.f,
+              p0z = p.N > 0 ? __ldg(xyz + 2) : 0.f;
+  float ox = p0x, oy = p0y, oz = p0z;
+  int32_t *idx = p.idx + (size_t)scene * p.npoint;
+  float *nxyz = p.new_xyz ? p.new_xyz + (size_t)scene * p.npoint * 3 : nullptr;
+  const bool writer = (rank == 0 && tid == 0);
+  if (writer && p.npoint > 0) {
+    idx[0] = 0;
+    if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
+  }
+  if (C > 1) cluster.sync();  // peers' shared memory must exist before the first DSMEM store
+  else __syncthreads();
+
+  for (int j = 1; j < p.npoint; ++j) {
+    const int buf = j & 1;
+    float best = -1.0f;
+    int bs = 0;
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      float d;
+      if (XYZ_REGS) d = sqdist_ref(x[s], y[s], z[s], ox, oy, oz);
+      else d = sqdist_ref(sx[s * THREADS + tid], sy[s * THREADS + tid], sz[s * THREADS + tid], ox, oy, oz);
+      const float d2 = fminf(d, t[s]);
+      t[s] = d2;
+      if (d2 > best) { best = d2; bs = s; }   // strict '>': lowest slot (= lowest v) wins ties
+    }
+    // ---- warp arg-max: max distance bits, then min virtual index ---------------------------
+    const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;  // 0 = "no valid point"
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
+    const unsigned myv = v0 + bs;
+    const unsigned wv = __reduce_min_sync(0xffffffffu, key == wmax ? myv : 0xffffffffu);
+    if (key == wmax && myv == wv) {            // exactly one lane
+      w_key[buf][warp] = wmax;
+      w_v[buf][warp] = wv;
+      w_x[buf][warp] = sx[bs * THREADS + tid];
+      w_y[buf][warp] = sy[bs * THREADS + tid];
+      w_z[buf][warp] = sz[bs * THREADS + tid];
+    }
+    __syncthreads();
+    // ---- CTA arg-max, computed redundantly by every warp ------------------------------------
+    unsigned k2 = 0u, v2 = 0xffffffffu;
+    if (lane < NW) { k2 = w_key[buf][lane]; v2 = w_v[buf][lane]; }
+    unsigned bmax = __reduce_max_sync(0xffffffffu, k2);
+    unsigned bv = __reduce_min_sync(0xffffffffu, k2 == bmax ? v2 : 0xffffffffu);
+    int src = __ffs(__ballot_sync(0xffffffffu, lane < NW && k2 == bmax && v2 == bv)) - 1;
+    float wx = w_x[buf][src], wy = w_y[buf][src], wz = w_z[buf][src];
+    if (C > 1) {
+      // ---- push this CTA's candidate to every CTA of the cluster (DSMEM), then barrier -----
+      if (warp == 0 && lane < C) {
+        unsigned *rk = cluster.map_shared_rank(&c_key[buf][rank], lane);
+        unsigned *rv = cluster.map_shared_rank(&c_v[buf][rank], lane);
+        float *rx = cluster.map_shared_rank(&c_x[buf][rank], lane);
+        float *ry = cluster.map_shared_rank(&c_y[buf][rank], lane);
+        float *rz = cluster.map_shared_rank(&c_z[buf][rank], lane);
+        *rk = bmax; *rv = bv; *rx = wx; *ry = wy; *rz = wz;
+      }
+      cluster.sync();
+      unsigned k3 = 0u, v3 = 0xffffffffu;
+      if (lane < C) { k3 = c_key[buf][lane]; v3 = c_v[buf][lane]; }
+      bmax = __reduce_max_sync(0xffffffffu, k3);
+      bv = __reduce_min_sync(0xffffffffu, k3 == bmax ? v3 : 0xffffffffu);
+      src = __ffs(__ballot_sync(0xffffffffu, lane < C && k3 == bmax && v3 == bv)) - 1;
+      wx = c_x[buf][src]; wy = c_y[buf][src]; wz = c_z[buf][src];
+    }
+    int old;
+    if (bmax == 0u) { old = 0; ox = p0x; oy = p0y; oz = p0z; }
+    else { ox = wx; oy = wy; oz = wz; old = 0; }
+    if (writer) {
+      if (bmax != 0u) old = fps_v_to_k(bv, p.Q, p.T, p.log2T);
+      idx[j] = old;
+      if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
+    }
+  }
+  if (C > 1) cluster.sync();  // no CTA may exit while a peer can still store into its smem
+}
+
+template <int P, int THREADS, bool XYZ_REGS>
+static int launch_fps(const FpsParams &p, int B, int C, cudaStream_t stream) {
+  auto kern = fps_cluster_kernel<P, THREADS, XYZ_REGS>;
+  const size_t smem = (size_t)3 * P * THREADS * sizeof(float);
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (C > 8) SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, B, 1);
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPC_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  return SPC_OK;
+}
+
+// how many clusters of size C (512 threads, given smem) can be co-resident; cached per C
+template <int P, int THREADS, bool XYZ_REGS>
+static int max_active_clusters(int C) {
+  auto kern = fps_cluster_kernel<P, THREADS, XYZ_REGS>;
+  const size_t smem = (size_t)3 * P * THREADS * sizeof(float);
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (C > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, 1, 1);
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return n;
+}
+
+}  // namespace spc
+
+using namespace spc;
+
+#define FPS_CASE(PV, TH, REGS)                                         \
+  case PV: return launch_fps<PV, TH, REGS>(p, B, C, stream);
+
+extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint,
+                                           int32_t *idx, float *new_xyz, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
+  SPC_CHECK_ARG(xyz && (idx || npoint == 0 || B == 0), "fps: null pointer");
+  if (B == 0 || npoint == 0) return SPC_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FpsParams p;
+  p.xyz = xyz; p.idx = idx; p.new_xyz = new_xyz; p.N = N; p.npoint = npoint;
+  p.T = ref_opt_n_threads(N);
+  p.log2T = 0;
+  while ((1 << p.log2T) < p.T) ++p.log2T;
+  p.Q = (N + p.T - 1) / p.T;
+  const long long V = (long long)p.T * p.Q;
+
+  // ---- small clouds: one CTA of 256 threads -------------------------------------------------
+  if (V <= 256 * 16) {
+    const int C = 1;
+    const int need = (int)((V + 255) / 256);
+    const int P = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
+    switch (P) {
+      FPS_CASE(1, 256, true) FPS_CASE(2, 256, true) FPS_CASE(4, 256, true)
+      FPS_CASE(8, 256, true) FPS_CASE(16, 256, true)
+    }
+  }
+  // ---- clusters of 512-thread CTAs ------------------------------------------------------------
+  // Prefer the largest cluster that still lets all B scenes be co-resident (per-round latency,
+  // not throughput, is what the sequential rounds pay for); an env override helps tuning.
+  static int cached_max16 = -1, cached_max8 = -1;
+  if (cached_max16 < 0) cached_max16 = max_active_clusters<6, 512, true>(16);
+  if (cached_max8 < 0) cached_max8 = max_active_clusters<12, 512, true>(8);
+  int C = 8;
+  if (cached_max16 >= B && cached_max16 > 0) C = 16;
+  else if (cached_max8 >= B) C = 8;
+  else if (B * 4 <= kNumSMs) C = 4;
+  else C = 2;
+  if (const char *e = getenv("SPC_FPS_CLUSTER")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
+  int need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512));
+  while (need > 32 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
+  if (C == 16 && cached_max16 <= 0) {
+    set_error("fps: N=%d needs a 16-CTA cluster which this device cannot schedule", N);
+    return SPC_ERR_UNSUPPORTED;
+  }
+  if (need > 32) {
+    set_error("fps: N=%d exceeds the on-chip capacity of a 16-CTA cluster (max %d points)", N, 16 * 512 * 32);
+    return SPC_ERR_UNSUPPORTED;
+  }
+  while (C > 1 && need <= 1) { C /= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
+  static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
+  int P = 32;
+  for (int o : opts) if (o >= need) { P = o; break; }
+  switch (P) {
+    FPS_CASE(2, 512, true) FPS_CASE(3, 512, true) FPS_CASE(4, 512, true) FPS_CASE(5, 512, true)
+    FPS_CASE(6, 512, true) FPS_CASE(8, 512, true) FPS_CASE(10, 512, true) FPS_CASE(12, 512, true)
+    FPS_CASE(16, 512, true) FPS_CASE(20, 512, false) FPS_CASE(24, 512, false) FPS_CASE(32, 512, false)
+  }
+  set_error("fps: internal dispatch error");
+  return SPC_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,355 @@
+// group.cu -- gather_points / group_points and their backward passes (sm_100a).
+//
+// Replaces gather_points_kernel, gather_points_grad_kernel (reference sampling_gpu.cu:8-57) and
+// group_points_kernel, group_points_grad_kernel (reference group_points_gpu.cu:8-75).  The
+// reference launches one block per scene, stores with a stride of nsample floats between
+// adjacent threads and gathers 4 bytes at a time straight from L2.
+//
+// group_points is the HBM-bound op of the path (out = C*npoint*nsample floats).  Design:
+//  * a CTA stages CT whole channel rows (CT*N floats) of one scene in shared memory with ONE
+//    bulk-TMA copy (cp.async.bulk, completion on an mbarrier) -- the rows of a scene are
+//    contiguous in the (B,C,N) layout, so no tensor map is needed;
+//  * the random 4-byte gathers then hit shared memory instead of 32-byte L2 sectors, the index
+//    tile is read once per CTA with 16-byte loads and reused for all CT channels, and the
+//    output is written with coalesced 16-byte streaming stores (4 consecutive positions / thread);
+//  * rows that do not fit in shared memory (N > ~50k) fall back to read-only-cache gathers.
+// The backward pass mirrors it: CT accumulator rows live in shared memory, duplicates inside a
+// warp are pre-combined (warp-aggregated atomics, __match_any_sync) before a shared-memory
+// atomic, and rows are flushed with plain coalesced stores (or global atomics when the
+// position range had to be split across CTAs to fill the machine).
+#include "common.cuh"
+
+namespace spc {
+
+// ----------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy helpers (PTX)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA engine, 1-D): bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void st_cs_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// gather_points:  out[b,c,j] = points[b,c,idx[b,j]]      (tiny: C is 3 in SpaCap3D)
+// ----------------------------------------------------------------------------------------------
+__global__ void gather_points_kernel(const float *__restrict__ points,
+                                     const int32_t *__restrict__ idx, int C, int N, int M,
+                                     float *__restrict__ out) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int a = __ldg(idx + (size_t)b * M + j);
+  for (int c = blockIdx.y; c < C; c += gridDim.y)
+    out[((size_t)b * C + c) * M + j] = __ldg(points + ((size_t)b * C + c) * N + a);
+}
+
+__global__ void gather_points_grad_kernel(const float *__restrict__ grad_out,
+                                          const int32_t *__restrict__ idx, int C, int N, int M,
+                                          float *__restrict__ grad_points) {
+  const int b = blockIdx.z;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int a = __ldg(idx + (size_t)b * M + j);
+  for (int c = blockIdx.y; c < C; c += gridDim.y)
+    atomicAdd(grad_points + ((size_t)b * C + c) * N + a, __ldg(grad_out + ((size_t)b * C + c) * M + j));
+}
+
+// ----------------------------------------------------------------------------------------------
+// group_points forward
+// ----------------------------------------------------------------------------------------------
+constexpr int GP_THREADS = 512;
+
+// grid = (position chunks, channel tiles, B).  STAGED: rows in smem, else gathers via LDG.
+template <bool STAGED, bool VEC4>
+__global__ void __launch_bounds__(GP_THREADS) group_points_kernel(
+    const float *__restrict__ points, const int32_t *__restrict__ idx, int C, int N, int S, int CT,
+    int chunk, float *__restrict__ out) {
+  extern __shared__ __align__(128) float s_rows[];  // [CT][N]
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * CT;
+  const int ct = min(CT, C - c0);
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(S, p0 + chunk);
+  const float *src = points + ((size_t)b * C + c0) * N;
+  const int32_t *ix = idx + (size_t)b * S;
+  float *dst = out + ((size_t)b * C + c0) * S;
+  const int tid = threadIdx.x;
+
+  if (STAGED) {
+    const size_t bytes = (size_t)ct * N * sizeof(float);
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (bytes % 16 == 0);
+    if (bulk_ok) {
+      if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+      __syncthreads();
+      if (tid == 0) {
+        // expect_tx is limited to 2^20-1 bytes per call; our rows are <= 227 KB
+        mbar_expect_tx(&bar, (unsigned)bytes);
+        bulk_g2s(s_rows, src, (unsigned)bytes, &bar);
+      }
+      mbar_wait(&bar, 0);
+    } else {
+      for (size_t e = tid; e < (size_t)ct * N; e += GP_THREADS) s_rows[e] = __ldg(src + e);
+      __syncthreads();
+    }
+  }
+
+  if (VEC4) {
+    // S % 4 == 0 and chunk % 4 == 0: 4 consecutive positions per thread, 16-byte idx load + store
+    for (int t = p0 + tid * 4; t < p1; t += GP_THREADS * 4) {
+      const int4 i4 = __ldg(reinterpret_cast<const int4 *>(ix + t));
+#pragma unroll 4
+      for (int c = 0; c < ct; ++c) {
+        float a0, a1, a2, a3;
+        if (STAGED) {
+          const float *r = s_rows + (size_t)c * N;
+          a0 = r[i4.x]; a1 = r[i4.y]; a2 = r[i4.z]; a3 = r[i4.w];
+        } else {
+          const float *r = src + (size_t)c * N;
+          a0 = __ldg(r + i4.x); a1 = __ldg(r + i4.y); a2 = __ldg(r + i4.z); a3 = __ldg(r + i4.w);
+        }
+        st_cs_v4(dst + (size_t)c * S + t, a0, a1, a2, a3);
+      }
+    }
+  } else {
+    for (int t = p0 + tid; t < p1; t += GP_THREADS) {
+      const int i = __ldg(ix + t);
+      for (int c = 0; c < ct; ++c)
+        dst[(size_t)c * S + t] = STAGED ? s_rows[(size_t)c * N + i] : __ldg(src + (size_t)c * N + i);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// group_points backward:  grad_points[b,c,idx[b,t]] += grad_out[b,c,t]
+// ----------------------------------------------------------------------------------------------
+// Warp-aggregated add into a shared (or global) accumulator row: lanes holding the same index
+// are combined first, so the ball-query padding (one index repeated up to nsample times) costs
+// one atomic instead of a same-address serialisation.  `peers` = lanes with my index
+// (__match_any_sync, computed once per position and reused for every channel).
+__device__ __forceinline__ void warp_agg_add(float *row, int i, float v, unsigned peers) {
+  const unsigned lane = lane_id();
+  if (peers == (1u << lane)) {  // common case: my index is unique in the warp
+    atomicAdd(row + i, v);
+    return;
+  }
+  float sum = 0.f;
+  for (unsigned m = peers; m; m &= m - 1) sum += __shfl_sync(peers, v, __ffs(m) - 1);
+  if ((int)lane == __ffs(peers) - 1) atomicAdd(row + i, sum);
+}
+
+template <bool STAGED>
+__global__ void __launch_bounds__(GP_THREADS) group_points_grad_kernel(
+    const float *__restrict__ grad_out, const int32_t *__restrict__ idx, int C, int N, int S,
+    int CT, int chunk, int use_global_atomics, float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) float s_rows[];  // [CT][N] accumulators
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * CT;
+  const int ct = min(CT, C - c0);
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(S, p0 + chunk);
+  const float *g = grad_out + ((size_t)b * C + c0) * S;
+  const int32_t *ix = idx + (size_t)b * S;
+  float *dst = grad_points + ((size_t)b * C + c0) * N;
+  const int tid = threadIdx.x;
+
+  if (STAGED) {
+    for (int e = tid; e < ct * N; e += GP_THREADS) s_rows[e] = 0.f;
+    __syncthreads();
+  }
+  const int span = p1 - p0;
+  const int iters = (span + GP_THREADS - 1) / GP_THREADS;
+  for (int it = 0; it < iters; ++it) {
+    const int t = p0 + it * GP_THREADS + tid;
+    const bool active = t < p1;
+    const int i = active ? __ldg(ix + t) : 0;
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) continue;
+    const unsigned peers = __match_any_sync(act, i);
+    for (int c = 0; c < ct; ++c) {
+      const float v = __ldg(g + (size_t)c * S + t);
+      warp_agg_add(STAGED ? s_rows + (size_t)c * N : dst + (size_t)c * N, i, v, peers);
+    }
+  }
+  if (STAGED) {
+    __syncthreads();
+    if (use_global_atomics) {
+      for (int e = tid; e < ct * N; e += GP_THREADS) {
+        const float v = s_rows[e];
+        if (v != 0.f) atomicAdd(dst + e, v);
+      }
+    } else {
+      for (int e = tid; e < ct * N; e += GP_THREADS) dst[e] = s_rows[e];
+    }
+  }
+}
+
+// channel-tile / chunk heuristics shared by forward and backward
+struct GroupPlan {
+  bool staged;
+  int CT, chunk, nchunks;
+  size_t smem;
+};
+
+static GroupPlan plan_group(int B, int C, int N, int S, bool backward) {
+  GroupPlan g;
+  const size_t row = (size_t)N * sizeof(float);
+  const size_t budget = 200 * 1024;
+  g.staged = row <= budget && N > 0;
+  if (!g.staged) {
+    g.CT = 4;
+    g.smem = 0;
+  } else {
+    // rows per CTA: as many as fit in ~64 KB (several CTAs/SM) but at least one
+    int ct = (int)((64 * 1024) / row);
+    if (ct < 1) ct = 1;
+    if (ct > C) ct = C;
+    if (ct > 16) ct = 16;
+    g.CT = ct;
+    g.smem = (size_t)ct * row;
+  }
+  const int ctiles = ceil_div(C, g.CT);
+  // split the position range until the grid has ~2 waves, but keep chunks >= 4096 positions so
+  // that the per-CTA row staging is amortised
+  int nchunks = 1;
+  const long long want = 2LL * kNumSMs;
+  while ((long long)B * ctiles * nchunks < want && S / (nchunks * 2) >= 4096) nchunks *= 2;
+  if (backward && !g.staged) nchunks = max(nchunks, 1);
+  int chunk = ceil_div(S, nchunks);
+  chunk = (chunk + 3) & ~3;
+  g.chunk = chunk;
+  g.nchunks = ceil_div(S, chunk);
+  return g;
+}
+
+}  // namespace spc
+
+using namespace spc;
+
+extern "C" int spc_gather_points(const float *points, const int32_t *idx, int B, int C, int N,
+                                 int M, float *out, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && M >= 0, "gather_points: bad sizes");
+  if (B == 0 || C == 0 || M == 0) return SPC_OK;
+  SPC_CHECK_ARG(points && idx && out, "gather_points: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "gather_points: B too large");
+  dim3 grid(ceil_div(M, 256), min(C, 64), B);
+  gather_points_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(points, idx, C, N, M, out);
+  SPC_LAUNCH_CHECK("gather_points_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_gather_points_grad(const float *grad_out, const int32_t *idx, int B, int C,
+                                      int N, int M, float *grad_points, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && M >= 0, "gather_points_grad: bad sizes");
+  if (B == 0 || C == 0 || N == 0) return SPC_OK;
+  SPC_CHECK_ARG(grad_points && (M == 0 || (grad_out && idx)), "gather_points_grad: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "gather_points_grad: B too large");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), stream));
+  if (M == 0) return SPC_OK;
+  dim3 grid(ceil_div(M, 256), min(C, 64), B);
+  gather_points_grad_kernel<<<grid, 256, 0, stream>>>(grad_out, idx, C, N, M, grad_points);
+  SPC_LAUNCH_CHECK("gather_points_grad_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_group_points(const float *points, const int32_t *idx, int B, int C, int N,
+                                int npoint, int nsample, float *out, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && npoint >= 0 && nsample >= 0, "group_points: bad sizes");
+  const long long S64 = (long long)npoint * nsample;
+  SPC_CHECK_ARG(S64 < (1LL << 31), "group_points: npoint*nsample overflows int32");
+  const int S = (int)S64;
+  if (B == 0 || C == 0 || S == 0) return SPC_OK;
+  SPC_CHECK_ARG(points && idx && out, "group_points: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "group_points: B too large");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const GroupPlan g = plan_group(B, C, N, S, false);
+  const bool vec4 = (S % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  dim3 grid(g.nchunks, ceil_div(C, g.CT), B);
+  SPC_CHECK_ARG(grid.y <= 65535, "group_points: too many channel tiles");
+#define GP_LAUNCH(ST, V4)                                                                       \
+  do {                                                                                          \
+    if (g.smem > 40 * 1024)                                                                     \
+      SPC_CUDA(cudaFuncSetAttribute(group_points_kernel<ST, V4>,                                \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+    group_points_kernel<ST, V4><<<grid, GP_THREADS, g.smem, stream>>>(points, idx, C, N, S,     \
+                                                                      g.CT, g.chunk, out);      \
+  } while (0)
+  if (g.staged) { if (vec4) GP_LAUNCH(true, true); else GP_LAUNCH(true, false); }
+  else { if (vec4) GP_LAUNCH(false, true); else GP_LAUNCH(false, false); }
+  SPC_LAUNCH_CHECK("group_points_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_group_points_grad(const float *grad_out, const int32_t *idx, int B, int C,
+                                     int N, int npoint, int nsample, float *grad_points,
+                                     void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && npoint >= 0 && nsample >= 0, "group_points_grad: bad sizes");
+  const long long S64 = (long long)npoint * nsample;
+  SPC_CHECK_ARG(S64 < (1LL << 31), "group_points_grad: npoint*nsample overflows int32");
+  const int S = (int)S64;
+  if (B == 0 || C == 0 || N == 0) return SPC_OK;
+  SPC_CHECK_ARG(grad_points && (S == 0 || (grad_out && idx)), "group_points_grad: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "group_points_grad: B too large");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (S == 0) {
+    SPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), stream));
+    return SPC_OK;
+  }
+  const GroupPlan g = plan_group(B, C, N, S, true);
+  const int global_atomics = (!g.staged || g.nchunks > 1) ? 1 : 0;
+  if (global_atomics)
+    SPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), stream));
+  dim3 grid(g.nchunks, ceil_div(C, g.CT), B);
+  SPC_CHECK_ARG(grid.y <= 65535, "group_points_grad: too many channel tiles");
+  if (g.staged) {
+    if (g.smem > 40 * 1024)
+      SPC_CUDA(cudaFuncSetAttribute(group_points_grad_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    group_points_grad_kernel<true><<<grid, GP_THREADS, g.smem, stream>>>(
+        grad_out, idx, C, N, S, g.CT, g.chunk, global_atomics, grad_points);
+  } else {
+    group_points_grad_kernel<false><<<grid, GP_THREADS, 0, stream>>>(
+        grad_out, idx, C, N, S, g.CT, g.chunk, 1, grad_points);
+  }
+  SPC_LAUNCH_CHECK("group_points_grad_kernel");
+  return SPC_OK;
+}

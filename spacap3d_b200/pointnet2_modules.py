@@ -1,0 +1,210 @@
+"""Same public API as the reference's lib/pointnet2/pointnet2_modules.py: the set-abstraction
+and feature-propagation layers SpaCap3D's detector is built from
+(PointnetSAModuleVotes :165-276, PointnetFPModule :361-421; plus _PointnetSAModuleBase,
+PointnetSAModuleMSG, PointnetSAModule, PointnetSAModuleMSGVotes, PointnetLFPModuleMSG for API
+completeness).  Parameter trees (`mlp_module.layer{i}.conv/.bn.bn`, `mlp.layer{i}...`) are the
+reference's, so its checkpoints load unchanged.
+
+All point-set work runs on this package's sm_100a kernels via pointnet2_utils.
+"""
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils
+from . import pytorch_utils as pt_utils
+from . import _ext
+
+# When False every module runs the reference's exact op sequence (FPS -> gather -> ball query ->
+# 2x grouping -> cat -> MLP -> pool) through `_ext`; used by the parity tests and by
+# bench.py --impl reference, which swaps `_ext` for the reference's own extension.
+FAST_PATHS = True
+
+
+def _sample_centres(xyz, npoint, inds=None):
+    """FPS (unless indices are supplied) + gather of the sampled coordinates.
+    Returns (new_xyz (B,npoint,3) or None, inds)."""
+    if npoint is None:
+        return None, inds
+    needs_grad = torch.is_grad_enabled() and xyz.requires_grad
+    if inds is None and not needs_grad and FAST_PATHS:
+        # one kernel: the FPS epilogue already holds the winners' coordinates
+        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint)
+        return new_xyz, inds
+    if inds is None:
+        inds = pointnet2_utils.furthest_point_sample(xyz, npoint)
+    xyz_flipped = xyz.transpose(1, 2).contiguous()
+    new_xyz = pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
+    return new_xyz, inds
+
+
+def _pool_max(x):
+    """(B,C,npoint,nsample) -> (B,C,npoint)"""
+    return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
+def _build_groupers(npoint, radii, nsamples, mlps, bn, use_xyz, sample_uniformly):
+    groupers, nets = nn.ModuleList(), nn.ModuleList()
+    for radius, nsample, mlp_spec in zip(radii, nsamples, mlps):
+        groupers.append(
+            pointnet2_utils.QueryAndGroup(radius, nsample, use_xyz=use_xyz,
+                                          sample_uniformly=sample_uniformly)
+            if npoint is not None else pointnet2_utils.GroupAll(use_xyz))
+        if use_xyz:
+            mlp_spec[0] += 3          # mutates the caller's list, like the reference (:207-209)
+        nets.append(pt_utils.SharedMLP(mlp_spec, bn=bn))
+    return groupers, nets
+
+
+class _PointnetSAModuleBase(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.npoint = None
+        self.groupers = None
+        self.mlps = None
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None):
+        """xyz (B,N,3), features (B,C,N) -> new_xyz (B,npoint,3), new_features (B,sum C_k,npoint)"""
+        new_xyz, _ = _sample_centres(xyz, self.npoint)
+        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features)))
+                for grouper, mlp in zip(self.groupers, self.mlps)]
+        return new_xyz, torch.cat(outs, dim=1)
+
+
+class PointnetSAModuleMSG(_PointnetSAModuleBase):
+    """Set abstraction with multi-scale grouping."""
+
+    def __init__(self, *, npoint: int, radii: List[float], nsamples: List[int],
+                 mlps: List[List[int]], bn: bool = True, use_xyz: bool = True,
+                 sample_uniformly: bool = False):
+        super().__init__()
+        assert len(radii) == len(nsamples) == len(mlps)
+        self.npoint = npoint
+        self.groupers, self.mlps = _build_groupers(npoint, radii, nsamples, mlps, bn, use_xyz,
+                                                   sample_uniformly)
+
+
+class PointnetSAModule(PointnetSAModuleMSG):
+    """Single-scale set abstraction."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None,
+                 nsample: int = None, bn: bool = True, use_xyz: bool = True):
+        super().__init__(mlps=[mlp], npoint=npoint, radii=[radius], nsamples=[nsample], bn=bn,
+                         use_xyz=use_xyz)
+
+
+class PointnetSAModuleVotes(nn.Module):
+    """Set abstraction that also returns the sampled indices (VoteNet needs them for vote
+    supervision).  forward(xyz, features=None, inds=None) -> (new_xyz, new_features, inds)."""
+
+    def __init__(self, *, mlp: List[int], npoint: int = None, radius: float = None,
+                 nsample: int = None, bn: bool = True, use_xyz: bool = True,
+                 pooling: str = 'max', sigma: float = None, normalize_xyz: bool = False,
+                 sample_uniformly: bool = False, ret_unique_cnt: bool = False):
+        super().__init__()
+        self.npoint = npoint
+        self.radius = radius
+        self.nsample = nsample
+        self.pooling = pooling
+        self.use_xyz = use_xyz
+        self.sigma = sigma if sigma is not None else (self.radius / 2 if self.radius is not None else None)
+        self.normalize_xyz = normalize_xyz
+        self.ret_unique_cnt = ret_unique_cnt
+        if npoint is not None:
+            self.grouper = pointnet2_utils.QueryAndGroup(
+                radius, nsample, use_xyz=use_xyz, ret_grouped_xyz=True,
+                normalize_xyz=normalize_xyz, sample_uniformly=sample_uniformly,
+                ret_unique_cnt=ret_unique_cnt)
+        else:
+            self.grouper = pointnet2_utils.GroupAll(use_xyz, ret_grouped_xyz=True)
+        mlp_spec = mlp
+        if use_xyz and len(mlp_spec) > 0:
+            mlp_spec[0] += 3
+        self.mlp_module = pt_utils.SharedMLP(mlp_spec, bn=bn)
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, inds: torch.Tensor = None):
+        """xyz (B,N,3), features (B,C,N), inds (B,npoint) optional ->
+        new_xyz (B,npoint,3), new_features (B,mlp[-1],npoint), inds (B,npoint) int32"""
+        if inds is not None:
+            assert inds.shape[1] == self.npoint
+        new_xyz, inds = _sample_centres(xyz, self.npoint, inds)
+        grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        new_features = self.mlp_module(grouped_features)      # (B, mlp[-1], npoint, nsample)
+        if self.pooling == 'max':
+            new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        elif self.pooling == 'avg':
+            new_features = F.avg_pool2d(new_features, kernel_size=[1, new_features.size(3)])
+        elif self.pooling == 'rbf':
+            # radial-basis weighting of the neighbours, normalised by nsample
+            rbf = torch.exp(-1 * grouped_xyz.pow(2).sum(1, keepdim=False) / (self.sigma ** 2) / 2)
+            new_features = torch.sum(new_features * rbf.unsqueeze(1), -1, keepdim=True) / float(self.nsample)
+        new_features = new_features.squeeze(-1)
+        return new_xyz, new_features, inds
+
+
+class PointnetSAModuleMSGVotes(nn.Module):
+    """Multi-scale set abstraction returning the sampled indices."""
+
+    def __init__(self, *, mlps: List[List[int]], npoint: int, radii: List[float],
+                 nsamples: List[int], bn: bool = True, use_xyz: bool = True,
+                 sample_uniformly: bool = False):
+        super().__init__()
+        assert len(mlps) == len(nsamples) == len(radii)
+        self.npoint = npoint
+        self.groupers, self.mlps = _build_groupers(npoint, radii, nsamples, mlps, bn, use_xyz,
+                                                   sample_uniformly)
+
+    def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, inds: torch.Tensor = None):
+        new_xyz, inds = _sample_centres(xyz, self.npoint, inds)
+        outs = [_pool_max(mlp(grouper(xyz, new_xyz, features)))
+                for grouper, mlp in zip(self.groupers, self.mlps)]
+        return new_xyz, torch.cat(outs, dim=1), inds
+
+
+class PointnetFPModule(nn.Module):
+    """Feature propagation: inverse-distance 3-NN interpolation + skip concat + SharedMLP."""
+
+    def __init__(self, *, mlp: List[int], bn: bool = True):
+        super().__init__()
+        self.mlp = pt_utils.SharedMLP(mlp, bn=bn)
+
+    def forward(self, unknown: torch.Tensor, known: torch.Tensor, unknow_feats: torch.Tensor,
+                known_feats: torch.Tensor) -> torch.Tensor:
+        """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m)
+        -> (B,mlp[-1],n)"""
+        if known is not None:
+            dist, idx = pointnet2_utils.three_nn(unknown, known)
+            dist_recip = 1.0 / (dist + 1e-8)
+            norm = torch.sum(dist_recip, dim=2, keepdim=True)
+            weight = dist_recip / norm
+            interpolated_feats = pointnet2_utils.three_interpolate(known_feats, idx, weight)
+        else:
+            interpolated_feats = known_feats.expand(*known_feats.size()[0:2], unknown.size(1))
+        new_features = interpolated_feats if unknow_feats is None else \
+            torch.cat([interpolated_feats, unknow_feats], dim=1)
+        return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+
+class PointnetLFPModuleMSG(nn.Module):
+    """Learnable feature propagation (group features1 around xyz2, MLP, pool, post-MLP)."""
+
+    def __init__(self, *, mlps: List[List[int]], radii: List[float], nsamples: List[int],
+                 post_mlp: List[int], bn: bool = True, use_xyz: bool = True,
+                 sample_uniformly: bool = False):
+        super().__init__()
+        assert len(mlps) == len(nsamples) == len(radii)
+        self.post_mlp = pt_utils.SharedMLP(post_mlp, bn=bn)
+        self.groupers, self.mlps = _build_groupers(0, radii, nsamples, mlps, bn, use_xyz,
+                                                   sample_uniformly)
+
+    def forward(self, xyz2: torch.Tensor, xyz1: torch.Tensor, features2: torch.Tensor,
+                features1: torch.Tensor) -> torch.Tensor:
+        outs = []
+        for grouper, mlp in zip(self.groupers, self.mlps):
+            new_features = _pool_max(mlp(grouper(xyz1, xyz2, features1)))
+            if features2 is not None:
+                new_features = torch.cat([new_features, features2], dim=1)
+            outs.append(self.post_mlp(new_features.unsqueeze(-1)))
+        return torch.cat(outs, dim=1).squeeze(-1)

@@ -1,0 +1,176 @@
+"""Seeded op-level test cases shared by oracle/make_golden.py (reference CUDA ext on a B200),
+tests/test_oracle_golden.py (C oracle vs golden, CPU) and tests/test_ops_gpu.py (our CUDA vs both).
+
+Every case is a dict of numpy inputs; `sha` pins the exact input bytes so a drifting RNG is
+caught instead of silently comparing different problems.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from spacap3d_b200.scenes import make_scene_xyz  # noqa: E402
+
+
+def sha(*arrays):
+    h = hashlib.sha1()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def _lattice(n_side, spacing=0.25, offset=0.0):
+    g = np.arange(n_side, dtype=np.float32) * np.float32(spacing) - np.float32(offset)
+    p = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    return np.ascontiguousarray(p, np.float32)
+
+
+# ------------------------------------------------------------------ FPS ---------------------
+def fps_cases():
+    c = {}
+    rng = np.random.default_rng(101)
+    c["tiny_n9"] = (rng.standard_normal((2, 9, 3)).astype(np.float32), 4)
+    c["n1"] = (rng.standard_normal((1, 1, 3)).astype(np.float32), 3)
+    c["n2"] = (rng.standard_normal((2, 2, 3)).astype(np.float32), 2)
+    c["n300_T256"] = (rng.uniform(-2, 2, (2, 300, 3)).astype(np.float32), 64)
+    c["n513"] = (rng.uniform(-2, 2, (1, 513, 3)).astype(np.float32), 200)
+    c["n1000_T512"] = (rng.uniform(-3, 3, (3, 1000, 3)).astype(np.float32), 256)
+    c["m_gt_n"] = (rng.uniform(-1, 1, (2, 20, 3)).astype(np.float32), 32)
+    # duplicates: 600 distinct points resampled to 2048, npoint beyond #distinct => zero-distance ties
+    base = rng.uniform(-3, 3, (2, 600, 3)).astype(np.float32)
+    pick = rng.integers(0, 600, (2, 2048))
+    dup = np.take_along_axis(base, pick[..., None].repeat(3, -1), 1)
+    c["dup_2048"] = (np.ascontiguousarray(dup), 1024)
+    # lattice: massive exact ties between distinct points (tie-break = bit-reversed thread id, F4)
+    lat = _lattice(16, 0.25, 1.875)
+    c["lattice_4096"] = (np.stack([lat, lat[::-1].copy()], 0), 512)
+    lat5 = _lattice(5, 0.5, 1.0)
+    c["lattice_125"] = (lat5[None].copy(), 125)
+    # near-origin skip (F5): |p|^2 <= 1e-3 never selected / never updated; index 0 itself near origin
+    near = rng.uniform(-0.02, 0.02, (2, 1500, 3)).astype(np.float32)
+    far = rng.uniform(-2, 2, (2, 1500, 3)).astype(np.float32)
+    mix = np.where(rng.random((2, 1500, 1)) < 0.4, near, far).astype(np.float32)
+    mix[0, 0] = [0.001, -0.002, 0.0005]
+    # points sitting right at the threshold |p|^2 ~ 1e-3
+    thr = np.sqrt(np.float32(1e-3) / np.float32(3.0))
+    for t in range(40):
+        mix[1, 10 + t] = np.float32(thr) * (1 + (t - 20) * 1e-7) * np.array([1, 1, 1], np.float32)
+    c["origin_mix"] = (np.ascontiguousarray(mix), 700)
+    c["all_skipped"] = (rng.uniform(-0.01, 0.01, (2, 64, 3)).astype(np.float32), 8)
+    # the BASELINE shape: 40k-point room scenes, one with duplicates (resampled with replacement)
+    sc = np.stack([make_scene_xyz(11, 40000, with_replacement=False),
+                   make_scene_xyz(12, 40000, with_replacement=True)], 0)
+    c["scene_40k"] = (sc, 2048)
+    return c
+
+
+def fps_follow_on(xyz, idx, npoint):
+    """new_xyz gathered with idx, as the SA module does (pointnet2_modules.py:240-242)."""
+    return np.take_along_axis(xyz, idx[..., None].astype(np.int64).repeat(3, -1), 1)[:, :npoint]
+
+
+# ------------------------------------------------------------------ ball query --------------
+def ball_query_cases():
+    """name -> (new_xyz, xyz, radius, nsample)"""
+    c = {}
+    rng = np.random.default_rng(202)
+    xyz = rng.uniform(-1, 1, (2, 500, 3)).astype(np.float32)
+    new = rng.uniform(-1.5, 1.5, (2, 70, 3)).astype(np.float32)  # some centres have empty balls
+    c["rand_small_r"] = (new, xyz, 0.15, 16)
+    c["rand_big_r"] = (new, xyz, 5.0, 32)            # every ball full after 32 points
+    c["nsample1"] = (new, xyz, 0.4, 1)
+    c["nsample_gt_n"] = (new[:, :10].copy(), xyz[:, :20].copy(), 0.8, 48)
+    lat = _lattice(8, 0.25, 0.875)
+    c["lattice_boundary"] = (lat[None, ::7].copy(), lat[None].copy(), 0.25, 8)  # d2 == r2 exactly: not a hit
+    c["lattice_boundary2"] = (lat[None, ::5].copy(), lat[None].copy(), 0.5, 64)
+    c["n33"] = (rng.uniform(-1, 1, (3, 5, 3)).astype(np.float32),
+                rng.uniform(-1, 1, (3, 33, 3)).astype(np.float32), 0.9, 7)
+    sc = np.stack([make_scene_xyz(21, 40000, with_replacement=False),
+                   make_scene_xyz(22, 40000, with_replacement=True)], 0)
+    # centres: a strided subset of the cloud itself (what FPS would return is checked elsewhere)
+    new_sc = np.ascontiguousarray(sc[:, ::40][:, :1000])
+    c["scene_sa1"] = (new_sc, sc, 0.2, 64)
+    sub = np.ascontiguousarray(sc[:, ::20])            # 2000 pts
+    c["scene_sa2"] = (np.ascontiguousarray(sub[:, ::2]), sub, 0.4, 32)
+    c["scene_sa4"] = (np.ascontiguousarray(sub[:, ::8][:, :256]), np.ascontiguousarray(sub[:, :512]), 1.2, 16)
+    return c
+
+
+# ------------------------------------------------------------------ three_nn ----------------
+def three_nn_cases():
+    """name -> (unknown, known)"""
+    c = {}
+    rng = np.random.default_rng(303)
+    c["fp1"] = (rng.uniform(-3, 3, (2, 512, 3)).astype(np.float32),
+                rng.uniform(-3, 3, (2, 256, 3)).astype(np.float32))
+    c["fp2"] = (rng.uniform(-3, 3, (2, 1024, 3)).astype(np.float32),
+                rng.uniform(-3, 3, (2, 512, 3)).astype(np.float32))
+    c["m2"] = (rng.standard_normal((1, 17, 3)).astype(np.float32),
+               rng.standard_normal((1, 2, 3)).astype(np.float32))
+    c["m1"] = (rng.standard_normal((2, 5, 3)).astype(np.float32),
+               rng.standard_normal((2, 1, 3)).astype(np.float32))
+    lat = _lattice(6, 0.5, 1.25)
+    c["lattice_ties"] = (lat[None, ::3].copy() + np.float32(0.25), lat[None].copy())
+    known = rng.uniform(-1, 1, (1, 300, 3)).astype(np.float32)
+    c["subset_zero_dist"] = (known[:, ::2].copy(), known)    # unknown is a subset: d = 0 exactly
+    return c
+
+
+# ------------------------------------------------------------------ index ops ---------------
+def gather_cases():
+    """name -> (points (B,C,N), idx (B,M))"""
+    rng = np.random.default_rng(404)
+    c = {}
+    c["xyz"] = (rng.standard_normal((2, 3, 1000)).astype(np.float32),
+                rng.integers(0, 1000, (2, 256)).astype(np.int32))
+    c["c7_dups"] = (rng.standard_normal((3, 7, 50)).astype(np.float32),
+                    rng.integers(0, 50, (3, 120)).astype(np.int32))
+    c["m1"] = (rng.standard_normal((1, 2, 9)).astype(np.float32), np.array([[4]], np.int32))
+    return c
+
+
+def group_cases():
+    """name -> (points (B,C,N), idx (B,np,ns))"""
+    rng = np.random.default_rng(505)
+    c = {}
+    c["sa_like"] = (rng.standard_normal((2, 16, 2048)).astype(np.float32),
+                    rng.integers(0, 2048, (2, 128, 32)).astype(np.int32))
+    c["c3"] = (rng.standard_normal((2, 3, 500)).astype(np.float32),
+               rng.integers(0, 500, (2, 33, 7)).astype(np.int32))
+    c["c1_ns1"] = (rng.standard_normal((1, 1, 10)).astype(np.float32),
+                   rng.integers(0, 10, (1, 5, 1)).astype(np.int32))
+    idx = rng.integers(0, 300, (2, 64, 16)).astype(np.int32)
+    idx[:, :, 5:] = idx[:, :, :1]                     # ball-query style padding: one index repeated
+    c["padded"] = (rng.standard_normal((2, 130, 300)).astype(np.float32), idx)
+    c["odd"] = (rng.standard_normal((1, 5, 77)).astype(np.float32),
+                rng.integers(0, 77, (1, 13, 3)).astype(np.int32))
+    return c
+
+
+def interp_cases():
+    """name -> (points (B,C,m), idx (B,n,3), weight (B,n,3))"""
+    rng = np.random.default_rng(606)
+    c = {}
+    for name, (B, C, m, n) in {"fp1": (2, 256, 256, 512), "odd": (1, 5, 7, 13), "c1": (2, 1, 3, 4)}.items():
+        w = rng.uniform(0.01, 1, (B, n, 3)).astype(np.float32)
+        w = (w / w.sum(-1, keepdims=True)).astype(np.float32)
+        c[name] = (rng.standard_normal((B, C, m)).astype(np.float32),
+                   rng.integers(0, m, (B, n, 3)).astype(np.int32), w)
+    # the reference's own test fixture (pointnet2_test.py:18-30)
+    c["ref_test"] = (rng.standard_normal((1, 2, 4)).astype(np.float32),
+                     np.array([[[0, 1, 2], [1, 2, 3]]], np.int32),
+                     np.array([[[1, 1, 1], [2, 2, 2]]], np.float32))
+    return c
+
+
+def grad_for(tag, shape):
+    """Deterministic upstream gradient for a named case."""
+    seed = int(hashlib.sha1(tag.encode()).hexdigest()[:8], 16)
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)

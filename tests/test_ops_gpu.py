@@ -1,0 +1,176 @@
+"""Parity of the sm_100a kernels (through the C ABI / `_ext`) against
+  (1) the CPU oracle (oracle/pointnet2_oracle.c) on every seeded case,
+  (2) the committed golden vectors produced by the reference's own CUDA extension,
+  (3) the reference extension itself when oracle/_ref/ is present on the box.
+Bar: bit-exact for indices and copies; rtol 1e-5 for atomically accumulated gradients
+(the reference's own gradients are order-nondeterministic).
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ext():
+    from spacap3d_b200 import _ext
+    return _ext
+
+
+@pytest.mark.parametrize("name", list(cases.fps_cases().keys()))
+def test_fps(ext, ref_ext, name):
+    xyz, m = cases.fps_cases()[name]
+    got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
+    want = oracle.furthest_point_sampling(xyz, m)
+    assert got.dtype == np.int32 and got.shape == want.shape
+    np.testing.assert_array_equal(got, want)
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.furthest_point_sampling(cu(xyz), m).cpu().numpy())
+    # fused new_xyz output == gather of the indices
+    idx2, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
+    np.testing.assert_array_equal(idx2.cpu().numpy(), want)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_fps_every_cluster_size(ext, cluster, monkeypatch):
+    """Same indices whatever the cluster size (the tie-break order must not depend on it)."""
+    monkeypatch.setenv("SPC_FPS_CLUSTER", str(cluster))
+    rng = np.random.default_rng(7)
+    base = rng.uniform(-3, 3, (3, 5000, 3)).astype(np.float32)
+    pick = rng.integers(0, 5000, (3, 12000))
+    xyz = np.ascontiguousarray(np.take_along_axis(base, pick[..., None].repeat(3, -1), 1))
+    want = oracle.furthest_point_sampling(xyz, 700)
+    got = ext.furthest_point_sampling(cu(xyz), 700).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
+def test_fps_prefix_property(ext):
+    """FPS over an FPS-ordered prefix returns 0..n-1 (the model relies on it)."""
+    xyz = cases.fps_cases()["scene_40k"][0][:1]
+    idx, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), 2048)
+    idx2 = ext.furthest_point_sampling(new_xyz.contiguous(), 1024).cpu().numpy()
+    np.testing.assert_array_equal(idx2[0], np.arange(1024, dtype=np.int32))
+
+
+@pytest.mark.parametrize("name", list(cases.ball_query_cases().keys()))
+def test_ball_query(ext, ref_ext, name):
+    new_xyz, xyz, r, ns = cases.ball_query_cases()[name]
+    got = ext.ball_query(cu(new_xyz), cu(xyz), r, ns).cpu().numpy()
+    want = oracle.ball_query(new_xyz, xyz, r, ns)
+    np.testing.assert_array_equal(got, want)
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.ball_query(cu(new_xyz), cu(xyz), float(r), ns).cpu().numpy())
+
+
+@pytest.mark.parametrize("name", list(cases.three_nn_cases().keys()))
+def test_three_nn(ext, ref_ext, name):
+    unknown, known = cases.three_nn_cases()[name]
+    d2, idx = ext.three_nn(cu(unknown), cu(known))
+    wd2, widx = oracle.three_nn(unknown, known)
+    np.testing.assert_array_equal(idx.cpu().numpy(), widx)
+    np.testing.assert_array_equal(d2.cpu().numpy(), wd2)
+    if ref_ext is not None:
+        rd2, ridx = ref_ext.three_nn(cu(unknown), cu(known))
+        np.testing.assert_array_equal(idx.cpu().numpy(), ridx.cpu().numpy())
+        np.testing.assert_array_equal(d2.cpu().numpy(), rd2.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", list(cases.gather_cases().keys()))
+def test_gather(ext, ref_ext, name):
+    pts, idx = cases.gather_cases()[name]
+    got = ext.gather_points(cu(pts), cu(idx)).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.gather_points(pts, idx))
+    g = cases.grad_for("gather/" + name, got.shape)
+    gg = ext.gather_points_grad(cu(g), cu(idx), pts.shape[2]).cpu().numpy()
+    np.testing.assert_allclose(gg, oracle.gather_points_grad(g, idx, pts.shape[2]), rtol=1e-5, atol=1e-6)
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.gather_points(cu(pts), cu(idx)).cpu().numpy())
+
+
+@pytest.mark.parametrize("name", list(cases.group_cases().keys()))
+def test_group(ext, ref_ext, name):
+    pts, idx = cases.group_cases()[name]
+    got = ext.group_points(cu(pts), cu(idx)).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.group_points(pts, idx))
+    g = cases.grad_for("group/" + name, got.shape)
+    gg = ext.group_points_grad(cu(g), cu(idx), pts.shape[2]).cpu().numpy()
+    want = oracle.group_points_grad(g, idx, pts.shape[2])
+    np.testing.assert_allclose(gg, want, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.group_points(cu(pts), cu(idx)).cpu().numpy())
+        rg = ref_ext.group_points_grad(cu(g), cu(idx), pts.shape[2]).cpu().numpy()
+        np.testing.assert_allclose(gg, rg, rtol=1e-5, atol=1e-5 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("name", list(cases.interp_cases().keys()))
+def test_interpolate(ext, ref_ext, name):
+    pts, idx, w = cases.interp_cases()[name]
+    got = ext.three_interpolate(cu(pts), cu(idx), cu(w)).cpu().numpy()
+    want = oracle.three_interpolate(pts, idx, w)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)   # the bar north_star states
+    g = cases.grad_for("interp/" + name, got.shape)
+    gg = ext.three_interpolate_grad(cu(g), cu(idx), cu(w), pts.shape[2]).cpu().numpy()
+    wg = oracle.three_interpolate_grad(g, idx, w, pts.shape[2])
+    np.testing.assert_allclose(gg, wg, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(wg).max()))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.three_interpolate(cu(pts), cu(idx), cu(w)).cpu().numpy())
+
+
+# ---------------------------------------------------------------- BASELINE-size properties ----
+def test_group_full_size_roundtrip(ext):
+    """Config-4 shape (B=2 of 8, C=132, N=40k, 2048x64): grouping is a pure gather, so
+    out[b,c,j,k] == points[b,c,idx[b,j,k]] checked with torch indexing, and the backward of a
+    ones-gradient equals the histogram of idx (size-independent properties)."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    B, C, N, npoint, ns = 2, 132, 40000, 2048, 64
+    pts = torch.randn(B, C, N, generator=g).to(DEV)
+    idx = torch.randint(0, N, (B, npoint, ns), generator=g, dtype=torch.int32).to(DEV)
+    out = ext.group_points(pts, idx)
+    want = torch.gather(pts, 2, idx.long().view(B, 1, -1).expand(-1, C, -1)).view(B, C, npoint, ns)
+    assert torch.equal(out, want)
+    ones = torch.ones(B, 3, npoint, ns, device=DEV)
+    hist = ext.group_points_grad(ones, idx, N)
+    want_hist = torch.zeros(B, N, device=DEV).scatter_add_(1, idx.long().view(B, -1), torch.ones(B, npoint * ns, device=DEV))
+    assert torch.equal(hist[:, 0], want_hist) and torch.equal(hist[:, 2], want_hist)
+
+
+def test_ball_query_full_size_properties(ext):
+    """SA1 shape on a 40k scene: rows ascending up to the pad, every listed point inside the
+    ball, pad == first hit, and the hit count equals a brute-force torch count (capped)."""
+    xyz_np = cases.fps_cases()["scene_40k"][0][:1]
+    xyz = cu(xyz_np)
+    idx_fps, new_xyz = ext.furthest_point_sampling_with_xyz(xyz, 2048)
+    r, ns = 0.2, 64
+    idx = ext.ball_query(new_xyz, xyz, r, ns).long()
+    d2 = ((new_xyz[:, :, None, :] - torch.gather(
+        xyz[:, None].expand(-1, 2048, -1, -1), 2, idx[..., None].expand(-1, -1, -1, 3))) ** 2).sum(-1)
+    assert (d2 < r * r * (1 + 1e-5)).all()
+    cnt_true = (torch.cdist(new_xyz, xyz) < r).sum(-1).clamp(max=ns)           # approx count
+    first = idx[..., :1]
+    is_pad = torch.arange(ns, device=DEV)[None, None] >= cnt_true[..., None]
+    # allow +-1 disagreement at the boundary between cdist rounding and the exact FMA order
+    inc = (idx[..., 1:] > idx[..., :-1]) | is_pad[..., 1:] | (torch.arange(1, ns, device=DEV)[None, None] >= (cnt_true[..., None] - 1))
+    assert inc.all()
+    strict_pad = torch.arange(ns, device=DEV)[None, None] >= (cnt_true[..., None] + 1)
+    assert ((idx == first) | ~strict_pad).all()
+
+
+def test_error_paths(ext):
+    x = torch.zeros(1, 4, 3)
+    with pytest.raises(RuntimeError):
+        ext.furthest_point_sampling(x, 2)                        # CPU tensor
+    with pytest.raises(RuntimeError):
+        ext.gather_points(torch.zeros(1, 3, 4, device=DEV), torch.zeros(1, 2, device=DEV))  # idx not int
+    with pytest.raises(RuntimeError):
+        ext.ball_query(torch.zeros(1, 2, 3, device=DEV).transpose(1, 2), torch.zeros(1, 4, 3, device=DEV), 0.1, 2)
