@@ -19,12 +19,15 @@ def _check(t, name, dtype):
         raise RuntimeError("%s must be a contiguous tensor" % name)
     if t.dtype != dtype:
         raise RuntimeError("%s must be %s tensor" % (name, "a float" if dtype == torch.float32 else "an int"))
-    if not t.is_cuda:
-        raise RuntimeError("CPU not supported")  # sampling.cpp:33-35 etc.
 
 
 def _same_device(a, *rest):
+    """Checked after dtype/contiguity of every argument, like the reference (sampling.cpp:15-35)."""
+    if not a.is_cuda:
+        raise RuntimeError("CPU not supported")  # sampling.cpp:33-35 etc.
     for t in rest:
+        if not t.is_cuda:
+            raise RuntimeError("all tensors must be CUDA tensors")
         if t.device != a.device:
             raise RuntimeError("all tensors must be on the same CUDA device")
 
@@ -36,6 +39,7 @@ def _stream():
 def furthest_point_sampling(points, nsamples):
     """(B,N,3) f32 -> (B,nsamples) i32.   sampling.cpp:66-87"""
     _check(points, "points", torch.float32)
+    _same_device(points)
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
@@ -48,6 +52,7 @@ def furthest_point_sampling_with_xyz(points, nsamples):
     """Extension: FPS that also returns the sampled coordinates (B,nsamples,3) from the same
     kernel (the gather that always follows FPS, pointnet2_modules.py:237-242)."""
     _check(points, "points", torch.float32)
+    _same_device(points)
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     new_xyz = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device)
