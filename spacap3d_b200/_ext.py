@@ -18,7 +18,8 @@ def _check(t, name, dtype):
     if not t.is_contiguous():
         raise RuntimeError("%s must be a contiguous tensor" % name)
     if t.dtype != dtype:
-        raise RuntimeError("%s must be %s tensor" % (name, "a float" if dtype == torch.float32 else "an int"))
+        kind = {torch.float32: "a float", torch.int32: "an int"}.get(dtype, "a " + str(dtype))
+        raise RuntimeError("%s must be %s tensor" % (name, kind))
 
 
 def _same_device(a, *rest):
@@ -171,4 +172,49 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     with torch.cuda.device(grad_out.device):
         _lib.call("spc_three_interpolate_grad", grad_out.data_ptr(), idx.data_ptr(),
                   weight.data_ptr(), B, C, n, int(m), out.data_ptr(), _stream())
+    return out
+
+
+def sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, *, G=None, Hc=None, feat=None, W0=None,
+                     b0=None, radius=1.0):
+    """Fused set-abstraction forward (eval): gather + layer 0 + two tcgen05 1x1 convs + max-pool.
+    See spc_sa_fused_forward in include/spacap3d_ops.h.  Raises _lib.SpcUnsupported when the
+    library has no kernel for the shape (caller then uses the unfused CUDA ops)."""
+    _check(xyz, "xyz", torch.float32)
+    _check(new_xyz, "new_xyz", torch.float32)
+    _check(idx, "idx", torch.int32)
+    _check(W1, "W1", torch.bfloat16)
+    _check(W2, "W2", torch.bfloat16)
+    _check(b1, "b1", torch.float32)
+    _check(b2, "b2", torch.float32)
+    _same_device(xyz, new_xyz, idx, W1, b1, W2, b2)
+    B, n, _ = xyz.shape
+    _, npoint, nsample = idx.shape
+    C2, C1 = W1.shape
+    C3 = W2.shape[0]
+    assert W2.shape[1] == C2 and b1.numel() == C2 and b2.numel() == C3
+    if G is not None:
+        _check(G, "G", torch.float32)
+        _check(Hc, "Hc", torch.float32)
+        _same_device(xyz, G, Hc)
+        assert G.shape == (B, n, C1) and Hc.shape == (B, npoint, C1)
+        Cf, pG, pHc, pfeat, pW0, pb0 = 0, G.data_ptr(), Hc.data_ptr(), None, None, None
+    else:
+        _check(W0, "W0", torch.float32)
+        _check(b0, "b0", torch.float32)
+        Cf = 0
+        pfeat = None
+        if feat is not None:
+            _check(feat, "feat", torch.float32)
+            _same_device(xyz, feat)
+            Cf = feat.shape[1]
+            pfeat = feat.data_ptr()
+        assert W0.shape == (C1, 3 + Cf) and b0.numel() == C1
+        pG, pHc, pW0, pb0 = None, None, W0.data_ptr(), b0.data_ptr()
+    out = torch.empty((B, C3, npoint), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.call("spc_sa_fused_forward", xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
+                  pG, pHc, pfeat, pW0, pb0, int(Cf), float(radius), W1.data_ptr(), b1.data_ptr(),
+                  W2.data_ptr(), b2.data_ptr(), B, n, npoint, nsample, C1, C2, C3,
+                  out.data_ptr(), _stream())
     return out

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -25,6 +25,8 @@ SIGNATURES = {
     "spc_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
     "spc_three_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "spc_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
+    "spc_sa_fused_forward": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,
+                             _i, _i, _i, _i, _i, _i, _i, _p, _p],
 }
 
 _lib = None
@@ -57,9 +59,18 @@ def load():
     return lib
 
 
+UNSUPPORTED = 3
+
+
+class SpcUnsupported(SpcError):
+    """The library has no kernel for this shape (SPC_ERR_UNSUPPORTED); nothing was launched."""
+
+
 def call(name, *args):
     lib = load()
     status = getattr(lib, name)(*args)
+    if status == UNSUPPORTED:
+        raise SpcUnsupported("%s: %s" % (name, lib.spc_last_error().decode("utf-8", "replace")))
     if status != 0:
         raise SpcError("%s failed (status %d): %s" %
                        (name, status, lib.spc_last_error().decode("utf-8", "replace")))

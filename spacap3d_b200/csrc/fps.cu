@@ -21,6 +21,7 @@
 //  * the |p|^2 <= 1e-3 skip (sampling_gpu.cu:100-101, compared in double) is evaluated once at
 //    load time: skipped / out-of-range slots get min-distance -1 and can never win.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 

@@ -16,6 +16,7 @@ import torch.nn.functional as F
 from . import pointnet2_utils
 from . import pytorch_utils as pt_utils
 from . import _ext
+from . import _lib
 
 # When False every module runs the reference's exact op sequence (FPS -> gather -> ball query ->
 # 2x grouping -> cat -> MLP -> pool) through `_ext`; used by the parity tests and by
@@ -38,6 +39,56 @@ def _sample_centres(xyz, npoint, inds=None):
     xyz_flipped = xyz.transpose(1, 2).contiguous()
     new_xyz = pointnet2_utils.gather_operation(xyz_flipped, inds).transpose(1, 2).contiguous()
     return new_xyz, inds
+
+
+INLINE_MAX_FEATURES = 16   # raw feature channels the fused kernel evaluates in-line (layer 0)
+
+
+def _fold_conv_bn(block):
+    """(W (Cout,Cin) f32, b (Cout) f32) of one SharedMLP block with eval-mode BN folded in, or
+    None when the block is not conv[+bn]+ReLU."""
+    conv = getattr(block, "conv", None)
+    act = getattr(block, "activation", None)
+    if conv is None or not isinstance(act, nn.ReLU) or conv.kernel_size != (1, 1):
+        return None
+    W = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+    norm = getattr(block, "bn", None)
+    if norm is not None:
+        bn = norm.bn
+        if bn.running_mean is None:
+            return None
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        if conv.bias is not None:
+            shift = shift + conv.bias.detach() * scale
+        return W * scale[:, None], shift.float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=W.device)
+    return W, b
+
+
+class _FoldedMLP:
+    """Cache of the BN-folded weights of a 3-layer SharedMLP (refreshed when any parameter or
+    running statistic changes, tracked through tensor versions)."""
+
+    def __init__(self):
+        self.key = None
+        self.data = None
+
+    def get(self, mlp):
+        tensors = [t for t in list(mlp.parameters()) + list(mlp.buffers())]
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self.key:
+            self.key = key
+            self.data = None
+            blocks = list(mlp.children())
+            if len(blocks) == 3:
+                folded = [_fold_conv_bn(b) for b in blocks]
+                if all(f is not None for f in folded):
+                    (W0, b0), (W1, b1), (W2, b2) = folded
+                    self.data = (W0.contiguous(), b0.contiguous(),
+                                 W1.to(torch.bfloat16).contiguous(), b1.contiguous(),
+                                 W2.to(torch.bfloat16).contiguous(), b2.contiguous())
+        return self.data
 
 
 def _pool_max(x):
@@ -130,6 +181,9 @@ class PointnetSAModuleVotes(nn.Module):
         if inds is not None:
             assert inds.shape[1] == self.npoint
         new_xyz, inds = _sample_centres(xyz, self.npoint, inds)
+        fused = self._forward_fused(xyz, new_xyz, features)
+        if fused is not None:
+            return new_xyz, fused, inds
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         new_features = self.mlp_module(grouped_features)      # (B, mlp[-1], npoint, nsample)
         if self.pooling == 'max':
@@ -142,6 +196,43 @@ class PointnetSAModuleVotes(nn.Module):
             new_features = torch.sum(new_features * rbf.unsqueeze(1), -1, keepdim=True) / float(self.nsample)
         new_features = new_features.squeeze(-1)
         return new_xyz, new_features, inds
+
+
+    # -- fused eval path ---------------------------------------------------------------------------
+    def _forward_fused(self, xyz, new_xyz, features):
+        """ball query -> ONE kernel (gather, relative xyz, 3 x [1x1 conv + folded BN + ReLU] with
+        the wide convs on tcgen05, max-pool).  Eval mode without autograd only; returns None when
+        not applicable so that the caller runs the reference op sequence on the unfused kernels."""
+        if (not FAST_PATHS or self.training or torch.is_grad_enabled() or self.npoint is None
+                or self.pooling != 'max' or not self.use_xyz or not xyz.is_cuda
+                or not isinstance(self.grouper, pointnet2_utils.QueryAndGroup)
+                or self.grouper.sample_uniformly or (features is not None and features.dtype != torch.float32)):
+            return None
+        cache = self.__dict__.setdefault("_folded", _FoldedMLP())
+        folded = cache.get(self.mlp_module)
+        if folded is None:
+            return None
+        W0, b0, W1, b1, W2, b2 = folded
+        Cf = 0 if features is None else features.shape[1]
+        if W0.shape[1] != 3 + Cf:
+            return None
+        radius = float(self.radius) if self.normalize_xyz else 1.0
+        xyz = xyz.contiguous()
+        idx = pointnet2_utils.ball_query(self.radius, self.nsample, xyz, new_xyz)
+        try:
+            if Cf <= INLINE_MAX_FEATURES:
+                feat = None if features is None else features.contiguous()
+                return _ext.sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, feat=feat, W0=W0,
+                                             b0=b0, radius=radius)
+            # conv0 hoisted out of the grouping: per-point projection + per-centre bias
+            Wx = W0[:, :3] / radius
+            G = torch.matmul(features.transpose(1, 2), W0[:, 3:].t())
+            G += torch.matmul(xyz, Wx.t())
+            Hc = b0 - torch.matmul(new_xyz, Wx.t())
+            return _ext.sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, G=G.contiguous(),
+                                         Hc=Hc.contiguous())
+        except _lib.SpcUnsupported:
+            return None
 
 
 class PointnetSAModuleMSGVotes(nn.Module):
