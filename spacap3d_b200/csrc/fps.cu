@@ -10,9 +10,10 @@
 //  * per round: P fused distance/min updates per thread, a 2-instruction warp arg-max
 //    (redux.sync max on the distance bits, redux.sync min on the tie-break key), one
 //    __syncthreads for the CTA-level candidate table, then every CTA pushes its candidate
-//    (distance, key, x, y, z) into every peer's shared memory through DSMEM and one
-//    cluster barrier publishes it -- each CTA then reduces the C candidates redundantly, so
-//    the winner's coordinates are already on-chip for the next round;
+//    (distance, index, x, y, z) into every peer's shared memory with st.async, whose
+//    completion is counted on the peer's mbarrier (no cluster barrier, no fence) -- each CTA
+//    then reduces the C candidates redundantly, so the winner's coordinates are already
+//    on-chip for the next round;
 //  * bit-exactness with the reference's block-tree arg-max: among equal maxima the reference
 //    keeps the candidate with the smallest (bit-reversed thread id, k div T), T =
 //    opt_n_threads(N).  Points are assigned to threads in exactly that order
@@ -46,17 +47,79 @@ __device__ __forceinline__ int fps_v_to_k(unsigned v, int Q, int T, int log2T) {
   return (int)(q * (unsigned)T + res);
 }
 
+// ---- PTX helpers: cluster address mapping, mbarrier, async DSMEM store --------------------------
+__device__ __forceinline__ uint32_t fps_s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void fps_mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_s2u(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fps_mbar_arm(uint64_t *bar, unsigned tx_bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fps_s2u(bar)), "r"(tx_bytes)
+               : "memory");
+}
+// NB: plain (cta-scope) try_wait.  A cluster-scope acquire here compiles to an L1 invalidate
+// (CCTL.IVALL) on every poll; completion of a transaction barrier already makes the st.async
+// payload visible (same contract as a TMA load).
+__device__ __forceinline__ void fps_mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "FPS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra FPS_DONE;\n"
+      "bra FPS_WAIT;\n"
+      "FPS_DONE:\n"
+      "}\n" ::"r"(fps_s2u(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 16-byte + 4-byte remote stores into a peer CTA's shared memory; each store signals its bytes
+// on the peer's mbarrier (complete_tx), so the receiver needs no fence and no cluster barrier
+// (cg::cluster_group::sync() costs a MEMBAR.ALL.GPU + L1 invalidate per round: measured 40 % of
+// the kernel in the first version).
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t c,
+                                            uint32_t d, uint32_t remote_bar) {
+  asm volatile(
+      "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::
+          "r"(remote_addr),
+      "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+      : "memory");
+}
+__device__ __forceinline__ void st_async_b32(uint32_t remote_addr, uint32_t a, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(a), "r"(remote_bar)
+               : "memory");
+}
+
+// candidate record exchanged between warps / CTAs: 32 bytes, 16-byte aligned
+struct __align__(16) FpsCand {
+  unsigned key;   // distance bits + 1, 0 = "no valid point"
+  int k;          // point index
+  float x, y;
+  float z;
+  unsigned pad[3];
+};
+
 // XYZ_REGS: coordinates in registers (fast path); otherwise they are read from shared memory
 // every round (large-N fallback, P up to 32 with 512 threads).
+//
+// Tie-break without a second reduction: points are laid out so that the virtual index v grows
+// with (cluster rank, warp, lane, slot).  "Largest distance, then smallest v" therefore is
+// "largest key, then FIRST in (rank, warp, lane, slot) order" -- one redux.max + one ballot/ffs
+// per level, and the per-thread strict '>' keeps the lowest slot.
 template <int P, int THREADS, bool XYZ_REGS>
 __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams p) {
   constexpr int NW = THREADS / 32;
-  extern __shared__ float s_xyz[];  // [3][P][THREADS] SoA copy of this CTA's points
+  extern __shared__ float s_xyz[];  // [3][P][THREADS] SoA copy of this CTA's points + [P][THREADS] index
   float *sx = s_xyz, *sy = s_xyz + P * THREADS, *sz = s_xyz + 2 * P * THREADS;
-  __shared__ unsigned w_key[2][NW], w_v[2][NW];
-  __shared__ float w_x[2][NW], w_y[2][NW], w_z[2][NW];
-  __shared__ unsigned c_key[2][kMaxCluster], c_v[2][kMaxCluster];
-  __shared__ float c_x[2][kMaxCluster], c_y[2][kMaxCluster], c_z[2][kMaxCluster];
+  int *sk = reinterpret_cast<int *>(s_xyz + 3 * P * THREADS);
+  __shared__ FpsCand w_cand[2][NW];            // per-warp candidates (double buffered)
+  __shared__ FpsCand c_cand[2][kMaxCluster];   // per-CTA candidates, written by peers via DSMEM
+  __shared__ __align__(8) uint64_t c_bar[2];   // "all C candidates of this buffer have landed"
 
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned C = cluster.num_blocks();
@@ -74,8 +137,9 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
   for (int s = 0; s < P; ++s) {
     const unsigned v = v0 + s;
     float px = 0.f, py = 0.f, pz = 0.f, pt = -1.0f;
+    int k = 0;
     if (v < V) {
-      const int k = fps_v_to_k(v, p.Q, p.T, p.log2T);
+      k = fps_v_to_k(v, p.Q, p.T, p.log2T);
       if (k < p.N) {
         px = __ldg(xyz + 3 * k + 0);
         py = __ldg(xyz + 3 * k + 1);
@@ -87,23 +151,43 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
     sx[s * THREADS + tid] = px;
     sy[s * THREADS + tid] = py;
     sz[s * THREADS + tid] = pz;
+    sk[s * THREADS + tid] = k;
     if (XYZ_REGS) { x[s] = px; y[s] = py; z[s] = pz; }
     t[s] = pt;
   }
   // point 0 is always the first pick (sampling_gpu.cu:85-86) and the fallback when no valid
   // point exists (every thread reports best=-1, besti=0 => dists_i[0] == 0).
-  const float p0x = p.N > 0 ? __ldg(xyz + 0) : 0.f, p0y = p.N > 0 ? __ldg(xyz + 1) : 0.f,
-              p0z = p.N > 0 ? __ldg(xyz + 2) : 0.f;
+  const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float ox = p0x, oy = p0y, oz = p0z;
   int32_t *idx = p.idx + (size_t)scene * p.npoint;
   float *nxyz = p.new_xyz ? p.new_xyz + (size_t)scene * p.npoint * 3 : nullptr;
-  const bool writer = (rank == 0 && tid == 0);
-  if (writer && p.npoint > 0) {
+  // the output writer sits in the LAST warp so that the first warp (which drives the cluster
+  // exchange) never lags behind
+  const bool writer = (rank == 0 && tid == THREADS - 1);
+  if (writer) {
     idx[0] = 0;
     if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
   }
-  if (C > 1) cluster.sync();  // peers' shared memory must exist before the first DSMEM store
-  else __syncthreads();
+  const unsigned tx_bytes = 20u * C;
+  uint32_t r_slot0 = 0, r_slot1 = 0, r_bar0 = 0, r_bar1 = 0;   // my slot / barrier in peer `lane`
+  if (C > 1) {
+    if (tid == 0) {
+      fps_mbar_init(&c_bar[0], 1);
+      fps_mbar_init(&c_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fps_mbar_arm(&c_bar[0], tx_bytes);
+      fps_mbar_arm(&c_bar[1], tx_bytes);
+    }
+    cluster.sync();   // peers' barriers are initialised before anyone stores into them
+    if (warp == 0 && lane < C) {
+      r_slot0 = mapa_cluster(fps_s2u(&c_cand[0][rank]), lane);
+      r_slot1 = mapa_cluster(fps_s2u(&c_cand[1][rank]), lane);
+      r_bar0 = mapa_cluster(fps_s2u(&c_bar[0]), lane);
+      r_bar1 = mapa_cluster(fps_s2u(&c_bar[1]), lane);
+    }
+  } else {
+    __syncthreads();
+  }
 
   for (int j = 1; j < p.npoint; ++j) {
     const int buf = j & 1;
@@ -118,49 +202,58 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
       t[s] = d2;
       if (d2 > best) { best = d2; bs = s; }   // strict '>': lowest slot (= lowest v) wins ties
     }
-    // ---- warp arg-max: max distance bits, then min virtual index ---------------------------
-    const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;  // 0 = "no valid point"
+    // every lane fetches its own candidate (overlaps the reduction latency; no divergent chain)
+    const float mx = sx[bs * THREADS + tid], my = sy[bs * THREADS + tid], mz = sz[bs * THREADS + tid];
+    const int mk = sk[bs * THREADS + tid];
+    // ---- warp arg-max: redux.max on the distance bits; first lane among equals wins ----------
+    const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
     const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-    const unsigned myv = v0 + bs;
-    const unsigned wv = __reduce_min_sync(0xffffffffu, key == wmax ? myv : 0xffffffffu);
-    if (key == wmax && myv == wv) {            // exactly one lane
-      w_key[buf][warp] = wmax;
-      w_v[buf][warp] = wv;
-      w_x[buf][warp] = sx[bs * THREADS + tid];
-      w_y[buf][warp] = sy[bs * THREADS + tid];
-      w_z[buf][warp] = sz[bs * THREADS + tid];
+    const unsigned eq = __ballot_sync(0xffffffffu, key == wmax);
+    if (lane == (unsigned)(__ffs(eq) - 1)) {
+      FpsCand *e = &w_cand[buf][warp];
+      *reinterpret_cast<uint4 *>(e) = make_uint4(wmax, (unsigned)mk, __float_as_uint(mx), __float_as_uint(my));
+      e->z = mz;
     }
     __syncthreads();
-    // ---- CTA arg-max, computed redundantly by every warp ------------------------------------
-    unsigned k2 = 0u, v2 = 0xffffffffu;
-    if (lane < NW) { k2 = w_key[buf][lane]; v2 = w_v[buf][lane]; }
-    unsigned bmax = __reduce_max_sync(0xffffffffu, k2);
-    unsigned bv = __reduce_min_sync(0xffffffffu, k2 == bmax ? v2 : 0xffffffffu);
-    int src = __ffs(__ballot_sync(0xffffffffu, lane < NW && k2 == bmax && v2 == bv)) - 1;
-    float wx = w_x[buf][src], wy = w_y[buf][src], wz = w_z[buf][src];
-    if (C > 1) {
-      // ---- push this CTA's candidate to every CTA of the cluster (DSMEM), then barrier -----
-      if (warp == 0 && lane < C) {
-        unsigned *rk = cluster.map_shared_rank(&c_key[buf][rank], lane);
-        unsigned *rv = cluster.map_shared_rank(&c_v[buf][rank], lane);
-        float *rx = cluster.map_shared_rank(&c_x[buf][rank], lane);
-        float *ry = cluster.map_shared_rank(&c_y[buf][rank], lane);
-        float *rz = cluster.map_shared_rank(&c_z[buf][rank], lane);
-        *rk = bmax; *rv = bv; *rx = wx; *ry = wy; *rz = wz;
-      }
-      cluster.sync();
-      unsigned k3 = 0u, v3 = 0xffffffffu;
-      if (lane < C) { k3 = c_key[buf][lane]; v3 = c_v[buf][lane]; }
-      bmax = __reduce_max_sync(0xffffffffu, k3);
-      bv = __reduce_min_sync(0xffffffffu, k3 == bmax ? v3 : 0xffffffffu);
-      src = __ffs(__ballot_sync(0xffffffffu, lane < C && k3 == bmax && v3 == bv)) - 1;
-      wx = c_x[buf][src]; wy = c_y[buf][src]; wz = c_z[buf][src];
+    // ---- CTA arg-max, computed redundantly by every warp (first warp among equals wins) ------
+    uint4 e4 = make_uint4(0u, 0u, 0u, 0u);
+    float ez = 0.f;
+    if (lane < NW) {
+      e4 = *reinterpret_cast<const uint4 *>(&w_cand[buf][lane]);
+      ez = w_cand[buf][lane].z;
     }
-    int old;
-    if (bmax == 0u) { old = 0; ox = p0x; oy = p0y; oz = p0z; }
-    else { ox = wx; oy = wy; oz = wz; old = 0; }
+    unsigned bmax = __reduce_max_sync(0xffffffffu, e4.x);
+    int src = __ffs(__ballot_sync(0xffffffffu, lane < NW && e4.x == bmax)) - 1;
+    unsigned wk = __shfl_sync(0xffffffffu, e4.y, src);
+    unsigned wxb = __shfl_sync(0xffffffffu, e4.z, src);
+    unsigned wyb = __shfl_sync(0xffffffffu, e4.w, src);
+    float wz = __shfl_sync(0xffffffffu, ez, src);
+    if (C > 1) {
+      // ---- push this CTA's candidate to every CTA of the cluster; data + completion in one op --
+      if (warp == 0 && lane < C) {
+        const uint32_t rs = buf ? r_slot1 : r_slot0, rb = buf ? r_bar1 : r_bar0;
+        st_async_v4(rs, bmax, wk, wxb, wyb, rb);
+        st_async_b32(rs + 16, __float_as_uint(wz), rb);
+      }
+      fps_mbar_wait(&c_bar[buf], (unsigned)((j - 1) >> 1) & 1u);   // u-th use of this buffer
+      if (tid == 0) fps_mbar_arm(&c_bar[buf], tx_bytes);           // re-arm for round j+2
+      e4 = make_uint4(0u, 0u, 0u, 0u);
+      ez = 0.f;
+      if (lane < C) {
+        e4 = *reinterpret_cast<const uint4 *>(&c_cand[buf][lane]);
+        ez = c_cand[buf][lane].z;
+      }
+      bmax = __reduce_max_sync(0xffffffffu, e4.x);
+      src = __ffs(__ballot_sync(0xffffffffu, lane < C && e4.x == bmax)) - 1;
+      wk = __shfl_sync(0xffffffffu, e4.y, src);
+      wxb = __shfl_sync(0xffffffffu, e4.z, src);
+      wyb = __shfl_sync(0xffffffffu, e4.w, src);
+      wz = __shfl_sync(0xffffffffu, ez, src);
+    }
+    int old = 0;
+    if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
+    else { ox = __uint_as_float(wxb); oy = __uint_as_float(wyb); oz = wz; old = (int)wk; }
     if (writer) {
-      if (bmax != 0u) old = fps_v_to_k(bv, p.Q, p.T, p.log2T);
       idx[j] = old;
       if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
     }
@@ -171,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
 template <int P, int THREADS, bool XYZ_REGS>
 static int launch_fps(const FpsParams &p, int B, int C, cudaStream_t stream) {
   auto kern = fps_cluster_kernel<P, THREADS, XYZ_REGS>;
-  const size_t smem = (size_t)3 * P * THREADS * sizeof(float);
+  const size_t smem = (size_t)4 * P * THREADS * sizeof(float);
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (C > 8) SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -194,7 +287,7 @@ static int launch_fps(const FpsParams &p, int B, int C, cudaStream_t stream) {
 template <int P, int THREADS, bool XYZ_REGS>
 static int max_active_clusters(int C) {
   auto kern = fps_cluster_kernel<P, THREADS, XYZ_REGS>;
-  const size_t smem = (size_t)3 * P * THREADS * sizeof(float);
+  const size_t smem = (size_t)4 * P * THREADS * sizeof(float);
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (C > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   cudaLaunchConfig_t cfg = {};
