@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspacap3d_ops.so")
+# SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
+LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
 ABI_VERSION = 2
 
 _p = ctypes.c_void_p

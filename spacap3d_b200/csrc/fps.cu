@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
     // ---- warp arg-max: redux.max on the distance bits; first lane among equals wins ----------
     const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
     const unsigned wmax = __reduce_max_sync(0xffffffffu, key);
-    const unsigned eq = __ballot_sync(0xffffffffu, key == wmax);
-    if (lane == (unsigned)(__ffs(eq) - 1)) {
+    // first lane among equals: redux.min on the lane id (26 cycles vs 66 for ballot + ffs)
+    if (lane == __reduce_min_sync(0xffffffffu, key == wmax ? lane : 32u)) {
       FpsCand *e = &w_cand[buf][warp];
       *reinterpret_cast<uint4 *>(e) = make_uint4(wmax, (unsigned)mk, __float_as_uint(mx), __float_as_uint(my));
       e->z = mz;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
       ez = w_cand[buf][lane].z;
     }
     unsigned bmax = __reduce_max_sync(0xffffffffu, e4.x);
-    int src = __ffs(__ballot_sync(0xffffffffu, lane < NW && e4.x == bmax)) - 1;
+    unsigned src = __reduce_min_sync(0xffffffffu, (lane < NW && e4.x == bmax) ? lane : 32u);
     unsigned wk = __shfl_sync(0xffffffffu, e4.y, src);
     unsigned wxb = __shfl_sync(0xffffffffu, e4.z, src);
     unsigned wyb = __shfl_sync(0xffffffffu, e4.w, src);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
         ez = c_cand[buf][lane].z;
       }
       bmax = __reduce_max_sync(0xffffffffu, e4.x);
-      src = __ffs(__ballot_sync(0xffffffffu, lane < C && e4.x == bmax)) - 1;
+      src = __reduce_min_sync(0xffffffffu, (lane < C && e4.x == bmax) ? lane : 32u);
       wk = __shfl_sync(0xffffffffu, e4.y, src);
       wxb = __shfl_sync(0xffffffffu, e4.z, src);
       wyb = __shfl_sync(0xffffffffu, e4.w, src);
@@ -338,19 +338,17 @@ extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int n
     }
   }
   // ---- clusters of 512-thread CTAs ------------------------------------------------------------
-  // Prefer the largest cluster that still lets all B scenes be co-resident (per-round latency,
-  // not throughput, is what the sequential rounds pay for); an env override helps tuning.
+  // The rounds are latency-bound, so all B scenes should be co-resident.  Measured on B200
+  // (B=8, N=40k): C=8 0.81 us/round, C=16 1.03 (slower exchange across a non-portable cluster),
+  // C=4 1.19 (xyz no longer fits in registers) -> prefer 8; SPC_FPS_CLUSTER overrides for tuning.
   static int cached_max16 = -1, cached_max8 = -1;
-  if (cached_max16 < 0) cached_max16 = max_active_clusters<6, 512, true>(16);
-  if (cached_max8 < 0) cached_max8 = max_active_clusters<12, 512, true>(8);
+  if (cached_max8 < 0) cached_max8 = max_active_clusters<10, 512, true>(8);
   int C = 8;
-  if (cached_max16 >= B && cached_max16 > 0) C = 16;
-  else if (cached_max8 >= B) C = 8;
-  else if (B * 4 <= kNumSMs) C = 4;
-  else C = 2;
+  if (cached_max8 > 0 && cached_max8 < B) C = (B * 4 <= kNumSMs) ? 4 : 2;
   if (const char *e = getenv("SPC_FPS_CLUSTER")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
   int need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512));
   while (need > 32 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
+  if (C == 16 && cached_max16 < 0) cached_max16 = max_active_clusters<6, 512, true>(16);
   if (C == 16 && cached_max16 <= 0) {
     set_error("fps: N=%d needs a 16-CTA cluster which this device cannot schedule", N);
     return SPC_ERR_UNSUPPORTED;
