@@ -19,6 +19,7 @@
 #ifndef SPACAP3D_OPS_H
 #define SPACAP3D_OPS_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -43,6 +44,19 @@ const char *spc_last_error(void);
  * No global workspace: running min-distances live in registers / distributed shared memory. */
 int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                 float *new_xyz, void *stream);
+
+/* Same operator with an exact shortcut for FPS-ORDERED inputs (SA2..SA4 of the detector sample
+ * from the previous layer's FPS output, where the reference's result is 0..npoint-1 unless exact
+ * distance ties interfere -- the reference model relies on that, models/backbone_module.py:107-127).
+ * With hint_ordered != 0 and a workspace of spc_fps_workspace_bytes(B,N,npoint) bytes, two fully
+ * parallel kernels PROVE per scene whether FPS(xyz)[0:npoint] == 0..npoint-1 (every round's winner
+ * is the strict unique maximum, same fp32 arithmetic); proven scenes skip the npoint-1 sequential
+ * rounds, all others run the normal kernel.  Results are identical to spc_furthest_point_sampling
+ * in every case; the hint only affects speed. */
+size_t spc_fps_workspace_bytes(int B, int N, int npoint);
+int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, int32_t *idx,
+                                   float *new_xyz, int hint_ordered, void *workspace,
+                                   size_t workspace_bytes, void *stream);
 
 /* gather_points(points, idx)                             sampling.cpp:15-38, sampling_gpu.cu:8-30
  * points (B,C,N), idx (B,M) -> out (B,C,M) */

@@ -49,17 +49,28 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
-def furthest_point_sampling_with_xyz(points, nsamples):
+def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False):
     """Extension: FPS that also returns the sampled coordinates (B,nsamples,3) from the same
-    kernel (the gather that always follows FPS, pointnet2_modules.py:237-242)."""
+    kernel (the gather that always follows FPS, pointnet2_modules.py:237-242).
+
+    hint_ordered=True tells the library that `points` is probably itself an FPS output (SA2..SA4
+    sample from the previous layer's centres); it then PROVES, with two parallel kernels, whether
+    the result is 0..nsamples-1 and skips the sequential rounds for the scenes where it is.  The
+    returned indices are identical with or without the hint (spc_furthest_point_sampling_ex)."""
     _check(points, "points", torch.float32)
     _same_device(points)
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     new_xyz = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
-                  out.data_ptr(), new_xyz.data_ptr(), _stream())
+        if hint_ordered and 2 <= nsamples <= N:
+            nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
+            _lib.call("spc_furthest_point_sampling_ex", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), new_xyz.data_ptr(), 1, ws.data_ptr(), nbytes, _stream())
+        else:
+            _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), new_xyz.data_ptr(), _stream())
     return out, new_xyz
 
 

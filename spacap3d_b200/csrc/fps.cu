@@ -38,6 +38,7 @@ struct FpsParams {
   float *new_xyz;     // (B,npoint,3) or nullptr
   int N, npoint;
   int T, log2T, Q;    // reference thread count, its log2, ceil(N/T)
+  const int *ordered_ok;  // per scene: 1 = "FPS(xyz)[0:npoint] is provably 0..npoint-1" (or nullptr)
 };
 
 __device__ __forceinline__ int fps_v_to_k(unsigned v, int Q, int T, int log2T) {
@@ -131,6 +132,19 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
   const unsigned g = rank * THREADS + tid;      // thread id within the cluster
   const unsigned v0 = g * P;                    // first virtual index owned by this thread
   const unsigned V = (unsigned)p.T * (unsigned)p.Q;
+
+  // Verified shortcut (see fps_prefix_check_kernel): the input is an FPS-ordered prefix, so the
+  // npoint sequential rounds would return 0..npoint-1.  Every CTA of the cluster reads the same
+  // flag, so they all leave together.
+  if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {
+    int32_t *oidx = p.idx + (size_t)scene * p.npoint;
+    for (unsigned j = g; j < (unsigned)p.npoint; j += C * THREADS) oidx[j] = (int)j;
+    if (p.new_xyz) {
+      float *o = p.new_xyz + (size_t)scene * p.npoint * 3;
+      for (unsigned e = g; e < 3u * (unsigned)p.npoint; e += C * THREADS) o[e] = __ldg(xyz + e);
+    }
+    return;
+  }
 
   float x[P], y[P], z[P], t[P];
 #pragma unroll
@@ -261,6 +275,107 @@ __global__ void __launch_bounds__(THREADS, 1) fps_cluster_kernel(const FpsParams
   if (C > 1) cluster.sync();  // no CTA may exit while a peer can still store into its smem
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Verify in parallel what would be constructed sequentially".
+// SA2..SA4 of the detector run FPS on the OUTPUT of the previous FPS (an FPS-ordered point list),
+// where the answer is 0..npoint-1 unless exact distance ties interfere (the reference
+// model silently relies on this).  Whether FPS(xyz)[0:npoint] == identity can be CHECKED with no
+// sequential dependency: with the first j points selected, point j must be the unique maximum of
+// the running min-distance among all not-yet-selected points.  Kernel A computes
+// D[j] = min_{i<j} d(p_j, p_i) (what round j's winner scored); kernel B recomputes every point's
+// running min-distance and flags any k > j that reaches D[j] (a tie or a larger value -- then
+// the tie-break / order decides and the full kernel must run).  Same fp32 arithmetic as the
+// sequential kernel (sqdist_ref, fminf, temp = 1e10), so the proof is exact, not approximate.
+// Cost: N*npoint distance evaluations, fully parallel (~10 us for 2048 -> 1024 at B=8) instead
+// of npoint-1 sequential rounds (~290 us).
+// ------------------------------------------------------------------------------------------------
+__global__ void fps_fill_kernel(int *p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+constexpr int CHK_THREADS = 128;
+constexpr int CHK_TILE = 256;
+
+__device__ __forceinline__ bool fps_skipped(float x, float y, float z) {
+  const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+  return (double)mag <= 1e-3;
+}
+
+// D[b][j] = min(1e10, min_{i<j} d(p_j, p_i)) for j < npoint;   ok[b] = 0 if a prefix point other than
+// p_0 is one the reference never selects (|p|^2 <= 1e-3)
+__global__ void __launch_bounds__(CHK_THREADS) fps_prefix_dist_kernel(const float *__restrict__ xyz, int N,
+                                                                       int npoint, float *__restrict__ D,
+                                                                       int *__restrict__ ok) {
+  __shared__ float sx[CHK_TILE], sy[CHK_TILE], sz[CHK_TILE];
+  const int b = blockIdx.y;
+  const float *P = xyz + (size_t)b * N * 3;
+  const int j = blockIdx.x * CHK_THREADS + threadIdx.x;
+  const bool act = j < npoint;
+  const float px = act ? __ldg(P + 3 * j) : 0.f, py = act ? __ldg(P + 3 * j + 1) : 0.f,
+              pz = act ? __ldg(P + 3 * j + 2) : 0.f;
+  if (act && j > 0 && fps_skipped(px, py, pz)) ok[b] = 0;
+  float m = 1e10f;
+  const int jmax = min(npoint, (int)(blockIdx.x + 1) * CHK_THREADS);   // largest j of this block + 1
+  for (int base = 0; base < jmax - 1; base += CHK_TILE) {
+    const int tile = min(CHK_TILE, jmax - 1 - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tile * 3; e += CHK_THREADS) {
+      const float v = __ldg(P + (size_t)base * 3 + e);
+      const int pt = e / 3, c = e - pt * 3;
+      (c == 0 ? sx : c == 1 ? sy : sz)[pt] = v;
+    }
+    __syncthreads();
+    const int lim = min(tile, j - base);          // only i < j
+    for (int i = 0; i < lim; ++i) {
+      // the reference never updates temp from a skipped centre?  No: the CENTRE may be any point
+      // (only index 0 can be a skipped one, and it is used as a centre like any other)
+      m = fminf(sqdist_ref(px, py, pz, sx[i], sy[i], sz[i]), m);
+    }
+  }
+  if (act) {
+    D[(size_t)b * npoint + j] = m;
+    // a winner at distance 0 (duplicate of an earlier point) ties with every selected point
+    if (j > 0 && !(m > 0.f)) ok[b] = 0;
+  }
+}
+
+// ok[b] &= for all rounds j in [1, npoint) and all points k > j (not skipped):
+//            min(1e10, min_{i<j} d(p_k, p_i)) < D[j]
+__global__ void __launch_bounds__(CHK_THREADS) fps_prefix_check_kernel(const float *__restrict__ xyz, int N,
+                                                                        int npoint,
+                                                                        const float *__restrict__ D,
+                                                                        int *__restrict__ ok) {
+  __shared__ float sx[CHK_TILE], sy[CHK_TILE], sz[CHK_TILE], sd[CHK_TILE];
+  const int b = blockIdx.y;
+  const float *P = xyz + (size_t)b * N * 3;
+  const float *Db = D + (size_t)b * npoint;
+  const int k = blockIdx.x * CHK_THREADS + threadIdx.x;
+  const bool act = k < N;
+  const float px = act ? __ldg(P + 3 * k) : 0.f, py = act ? __ldg(P + 3 * k + 1) : 0.f,
+              pz = act ? __ldg(P + 3 * k + 2) : 0.f;
+  const bool cand = act && !fps_skipped(px, py, pz);   // skipped points are never candidates
+  float m = 1e10f;
+  bool bad = false;
+  for (int base = 0; base < npoint - 1; base += CHK_TILE) {
+    const int tile = min(CHK_TILE, npoint - 1 - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tile * 3; e += CHK_THREADS) {
+      const float v = __ldg(P + (size_t)base * 3 + e);
+      const int pt = e / 3, c = e - pt * 3;
+      (c == 0 ? sx : c == 1 ? sy : sz)[pt] = v;
+    }
+    for (int e = threadIdx.x; e < tile; e += CHK_THREADS) sd[e] = __ldg(Db + base + e + 1);   // D[j], j = i+1
+    __syncthreads();
+    for (int i = 0; i < tile; ++i) {
+      m = fminf(sqdist_ref(px, py, pz, sx[i], sy[i], sz[i]), m);
+      // round j = base+i+1 picks among points with index > j - 1 that are not yet selected
+      bad |= (k > base + i + 1) && (m >= sd[i]);
+    }
+  }
+  if (cand && bad) ok[b] = 0;   // benign race: every writer stores 0
+}
+
 template <int P, int THREADS, bool XYZ_REGS>
 static int launch_fps(const FpsParams &p, int B, int C, cudaStream_t stream) {
   auto kern = fps_cluster_kernel<P, THREADS, XYZ_REGS>;
@@ -313,8 +428,28 @@ using namespace spc;
 #define FPS_CASE(PV, TH, REGS)                                         \
   case PV: return launch_fps<PV, TH, REGS>(p, B, C, stream);
 
+static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
+                    int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_);
+
+extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
+  (void)N;
+  return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B) * 4;
+}
+
 extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint,
                                            int32_t *idx, float *new_xyz, void *stream_) {
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, 0, nullptr, 0, stream_);
+}
+
+extern "C" int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint,
+                                              int32_t *idx, float *new_xyz, int hint_ordered,
+                                              void *workspace, size_t workspace_bytes,
+                                              void *stream_) {
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, workspace, workspace_bytes, stream_);
+}
+
+static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
+                    int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   SPC_CHECK_ARG(xyz && (idx || npoint == 0 || B == 0), "fps: null pointer");
   if (B == 0 || npoint == 0) return SPC_OK;
@@ -325,6 +460,19 @@ extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int n
   p.log2T = 0;
   while ((1 << p.log2T) < p.T) ++p.log2T;
   p.Q = (N + p.T - 1) / p.T;
+  p.ordered_ok = nullptr;
+  // ---- optional verified shortcut for FPS-ordered inputs ---------------------------------------
+  if (hint_ordered && workspace && npoint >= 2 && npoint <= N &&
+      workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && B <= 65535 &&
+      (long long)N * npoint <= (1LL << 26)) {
+    float *D = reinterpret_cast<float *>(workspace);
+    int *ok = reinterpret_cast<int *>(D + (size_t)B * npoint);
+    fps_fill_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(ok, B, 1);
+    fps_prefix_dist_kernel<<<dim3(ceil_div(npoint, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok);
+    fps_prefix_check_kernel<<<dim3(ceil_div(N, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok);
+    SPC_LAUNCH_CHECK("fps_prefix_check");
+    p.ordered_ok = ok;
+  }
   const long long V = (long long)p.T * p.Q;
 
   // ---- small clouds: one CTA of 256 threads -------------------------------------------------
@@ -364,7 +512,7 @@ extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int n
   switch (P) {
     FPS_CASE(2, 512, true) FPS_CASE(3, 512, true) FPS_CASE(4, 512, true) FPS_CASE(5, 512, true)
     FPS_CASE(6, 512, true) FPS_CASE(8, 512, true) FPS_CASE(10, 512, true) FPS_CASE(12, 512, true)
-    FPS_CASE(16, 512, true) FPS_CASE(20, 512, false) FPS_CASE(24, 512, false) FPS_CASE(32, 512, false)
+    FPS_CASE(16, 512, true) FPS_CASE(20, 512, true) FPS_CASE(24, 512, false) FPS_CASE(32, 512, false)
   }
   set_error("fps: internal dispatch error");
   return SPC_ERR_UNSUPPORTED;

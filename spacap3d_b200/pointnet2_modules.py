@@ -31,8 +31,12 @@ def _sample_centres(xyz, npoint, inds=None):
         return None, inds
     needs_grad = torch.is_grad_enabled() and xyz.requires_grad
     if inds is None and not needs_grad and FAST_PATHS:
-        # one kernel: the FPS epilogue already holds the winners' coordinates
-        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint)
+        # one kernel: the FPS epilogue already holds the winners' coordinates.  Centres produced by
+        # an FPS are tagged so that the next layer can try the verified "already FPS-ordered"
+        # shortcut (exact: see spc_furthest_point_sampling_ex).
+        hint = bool(getattr(xyz, "_spc_fps_ordered", False))
+        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
+        new_xyz._spc_fps_ordered = True
         return new_xyz, inds
     if inds is None:
         inds = pointnet2_utils.furthest_point_sample(xyz, npoint)

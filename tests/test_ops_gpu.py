@@ -174,3 +174,37 @@ def test_error_paths(ext):
         ext.gather_points(torch.zeros(1, 3, 4, device=DEV), torch.zeros(1, 2, device=DEV))  # idx not int
     with pytest.raises(RuntimeError):
         ext.ball_query(torch.zeros(1, 2, 3, device=DEV).transpose(1, 2), torch.zeros(1, 4, 3, device=DEV), 0.1, 2)
+
+
+# ---------------------------------------------------------------- verified ordered-prefix path ---
+def _fps_hint(ext, xyz_t, m):
+    idx, new_xyz = ext.furthest_point_sampling_with_xyz(xyz_t, m, hint_ordered=True)
+    return idx.cpu().numpy(), new_xyz.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(cases.fps_cases().keys()))
+def test_fps_ordered_hint_never_changes_results(ext, name):
+    """The hint only affects speed: on arbitrary (unordered) inputs the proof fails and the
+    sequential kernel runs; results equal the oracle either way."""
+    xyz, m = cases.fps_cases()[name]
+    got, _ = _fps_hint(ext, cu(xyz), m)
+    np.testing.assert_array_equal(got, oracle.furthest_point_sampling(xyz, m))
+
+
+@pytest.mark.parametrize("name", ["scene_40k", "dup_2048", "lattice_4096", "origin_mix", "n1000_T512"])
+def test_fps_ordered_hint_on_fps_outputs(ext, name):
+    """Chained FPS as in SA1->SA2->SA3->SA4 (FPS of an FPS-ordered list): with and without the
+    hint, against the oracle -- including inputs with duplicates / lattice ties / skipped points,
+    where the answer is NOT the identity and the proof must fail."""
+    xyz, m = cases.fps_cases()[name]
+    cur = xyz
+    cur_t = cu(xyz)
+    n_next = m
+    for level in range(3):
+        idx, new_xyz = ext.furthest_point_sampling_with_xyz(cur_t, n_next, hint_ordered=(level > 0))
+        want = oracle.furthest_point_sampling(cur, n_next)
+        np.testing.assert_array_equal(idx.cpu().numpy(), want)
+        cur = cases.fps_follow_on(cur, want, n_next)
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(), cur)
+        cur_t = new_xyz.contiguous()
+        n_next = max(2, n_next // 2)
