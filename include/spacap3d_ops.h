@@ -74,6 +74,16 @@ int spc_gather_points_grad(const float *grad_out, const int32_t *idx, int B, int
 int spc_ball_query(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
                    int nsample, int32_t *idx, void *stream);
 
+/* Same operator, grid-accelerated for large clouds: with a workspace of
+ * spc_ball_query_workspace_bytes(B,N) bytes the scene is binned into cells of edge >= radius and
+ * each centre only visits its 3x3x3 neighbourhood; the hits are then ordered by point index, so
+ * the output is bit-identical to spc_ball_query (same distance arithmetic, same first-nsample /
+ * padding contract).  Small problems (and workspace == NULL) use the all-pairs kernel. */
+size_t spc_ball_query_workspace_bytes(int B, int N);
+int spc_ball_query_ex(const float *new_xyz, const float *xyz, int B, int N, int M, float radius,
+                      int nsample, int32_t *idx, void *workspace, size_t workspace_bytes,
+                      void *stream);
+
 /* group_points(points, idx)                              group_points.cpp:12-36, group_points_gpu.cu:8-39
  * points (B,C,N), idx (B,npoint,nsample) -> out (B,C,npoint,nsample) */
 int spc_group_points(const float *points, const int32_t *idx, int B, int C, int N, int npoint,

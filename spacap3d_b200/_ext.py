@@ -110,8 +110,14 @@ def ball_query(new_xyz, xyz, radius, nsample):
     N = xyz.shape[1]
     out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
     with torch.cuda.device(new_xyz.device):
-        _lib.call("spc_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius),
-                  int(nsample), out.data_ptr(), _stream())
+        if N >= 4096:      # large clouds: uniform-grid search (bit-identical output)
+            nbytes = _lib.load().spc_ball_query_workspace_bytes(B, N)
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=new_xyz.device)
+            _lib.call("spc_ball_query_ex", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius),
+                      int(nsample), out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        else:
+            _lib.call("spc_ball_query", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius),
+                      int(nsample), out.data_ptr(), _stream())
     return out
 
 

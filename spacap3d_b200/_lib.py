@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -22,6 +22,7 @@ SIGNATURES = {
     "spc_gather_points": [_p, _p, _i, _i, _i, _i, _p, _p],
     "spc_gather_points_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
     "spc_ball_query": [_p, _p, _i, _i, _i, _f, _i, _p, _p],
+    "spc_ball_query_ex": [_p, _p, _i, _i, _i, _f, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_group_points": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
@@ -53,6 +54,8 @@ def load():
     if lib.spc_abi_version() != ABI_VERSION:
         raise SpcError("libspacap3d_ops.so ABI %d != expected %d; rebuild" %
                        (lib.spc_abi_version(), ABI_VERSION))
+    lib.spc_ball_query_workspace_bytes.argtypes = [_i, _i]
+    lib.spc_ball_query_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_fps_workspace_bytes.argtypes = [_i, _i, _i]
     lib.spc_fps_workspace_bytes.restype = ctypes.c_size_t
     for name, argtypes in SIGNATURES.items():

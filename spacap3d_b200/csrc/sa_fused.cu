@@ -191,8 +191,16 @@ __device__ __forceinline__ void load_weights_blocked(uint8_t *dst, const __nv_bf
   }
 }
 
+// CTAs per SM the kernel is compiled for: two when TMEM columns and shared memory allow it (SA1
+// widths), so that one CTA's gather / epilogue overlaps the other's MMAs
+template <int C1, int C2, int C3>
+constexpr int sa_min_blocks() {
+  using L = SaSmem<C1, C2, C3>;
+  return (L::TMEM_COLS <= 256 && L::TOTAL_INLINE <= 100 * 1024) ? 2 : 1;
+}
+
 template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
-__global__ void __launch_bounds__(SA_THREADS, 1) sa_fused_kernel(const SaFusedParams p) {
+__global__ void __launch_bounds__(SA_THREADS, sa_min_blocks<C1, C2, C3>()) sa_fused_kernel(const SaFusedParams p) {
   using L = SaSmem<C1, C2, C3>;
   static_assert(C1 % 16 == 0 && C2 % 16 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "bad widths");
   static_assert(SA_ROWS % NS == 0 && (NS == 16 || NS == 32 || NS == 64), "bad nsample");
@@ -417,10 +425,13 @@ static int launch_sa(const SaFusedParams &p, cudaStream_t stream) {
   auto kern = sa_fused_kernel<C1, C2, C3, NS, MODE_PROJ>;
   const int smem = MODE_PROJ ? L::TOTAL_PROJ : L::TOTAL_INLINE;
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                cudaSharedmemCarveoutMaxShared));
   // CTAs per SM are bounded by TMEM columns (512 per SM) and shared memory
   int per_sm = 512 / L::TMEM_COLS;
   const int by_smem = (227 * 1024) / (smem + 2048);
   if (per_sm > by_smem) per_sm = by_smem;
+  if (per_sm > sa_min_blocks<C1, C2, C3>()) per_sm = sa_min_blocks<C1, C2, C3>();
   if (per_sm < 1) per_sm = 1;
   int grid = kNumSMs * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;

@@ -100,6 +100,20 @@ def ball_query_cases():
     sub = np.ascontiguousarray(sc[:, ::20])            # 2000 pts
     c["scene_sa2"] = (np.ascontiguousarray(sub[:, ::2]), sub, 0.4, 32)
     c["scene_sa4"] = (np.ascontiguousarray(sub[:, ::8][:, :256]), np.ascontiguousarray(sub[:, :512]), 1.2, 16)
+    # --- cases that take the uniform-grid path (N >= 4096 and N*M >= 2^22) -------------------------
+    rng = np.random.default_rng(909)
+    big = rng.uniform(-2, 2, (2, 6000, 3)).astype(np.float32)
+    cen = rng.uniform(-2.6, 2.6, (2, 800, 3)).astype(np.float32)          # some centres outside the bbox
+    c["grid_rand_r03"] = (cen, big, 0.3, 32)
+    c["grid_rand_tiny_r"] = (cen, big, 0.02, 8)                            # mostly empty balls
+    c["grid_rand_huge_r"] = (cen, big, 1.5, 64)                            # > 512 hits per centre: fallback scan
+    c["grid_rand_r_gt_extent"] = (cen, big, 9.0, 16)                       # one cell
+    lat = _lattice(17, 0.25, 2.0)                                          # 4913 points, spacing == radius
+    c["grid_lattice_boundary"] = (np.ascontiguousarray(lat[None, ::5][:, :900]), lat[None].copy(), 0.25, 16)
+    c["grid_lattice_r05"] = (np.ascontiguousarray(lat[None, ::5][:, :900]) + np.float32(0.125), lat[None].copy(), 0.5, 48)
+    flat = big.copy(); flat[..., 2] = np.float32(0.5)                      # degenerate (zero) extent in z
+    c["grid_flat"] = (np.ascontiguousarray(flat[:, ::7][:, :750]), flat, 0.25, 24)
+    c["scene_sa1_ns16"] = (new_sc, sc, 0.35, 16)                           # more hits than slots
     return c
 
 
