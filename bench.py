@@ -410,6 +410,15 @@ class OracleOps:
     def three_interpolate(self, p, i, w):
         return self._t(self.o.three_interpolate(p.numpy(), i.numpy(), w.numpy()))
 
+    def gather_points_grad(self, g, i, n):
+        return self._t(self.o.gather_points_grad(g.numpy(), i.numpy(), n))
+
+    def group_points_grad(self, g, i, n):
+        return self._t(self.o.group_points_grad(g.numpy(), i.numpy(), n))
+
+    def three_interpolate_grad(self, g, i, w, m):
+        return self._t(self.o.three_interpolate_grad(g.numpy(), i.numpy(), w.numpy(), m))
+
 
 class swapped_ops:
     """Route pointnet2_utils / pointnet2_modules to another op provider and force the
