@@ -40,7 +40,8 @@ FEATURE_DIM = 1          # xyz + height: the reference's default "xyz" input (SU
 CONFIG_ID = 2
 WORKLOAD = ("SpaCap3D xyz: batch 8 scenes x 40k pts per GPU, full detector forward "
             "(SA 2048/1024/512/256, FP1-2, voting, 256 proposals, box decode)")
-N_INPUT_SETS = 3         # distinct batches rotated through the timed loop
+N_INPUT_SETS = 26        # distinct batches rotated through the timed loops: 26 x 5.12 MB = 133 MB > 126 MB L2
+N_STREAMS = 2            # CUDA-graph replay streams (batches are independent; FPS uses 64 of 148 SMs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -275,6 +276,50 @@ def run_ours(args):
     launches_per_step = meter.launches // (args.steps + args.warmup)
     dev_s = sum(per_step) / 1e3
 
+    eager = {"ms_per_step": round(dev_s / args.steps * 1e3, 4),
+             "scenes_per_s_per_gpu": round(SCENES_PER_GPU * args.steps / dev_s, 2),
+             "note": "no CUDA graph, single stream, 256 MiB L2 flush between steps (excluded from the timing)"}
+    graph_info = None
+    if args.mode == "graph":
+        # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
+        from spacap3d_b200.pipeline import GraphedDetector
+        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS)
+
+        def timed_graph(submit, steps, warmup, sampler=None):
+            for i in range(warmup):
+                submit(i)
+            runner.wait_all()
+            torch.cuda.synchronize()
+            barrier()
+            if sampler:
+                sampler.start()
+            cur = torch.cuda.current_stream()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(cur)
+            runner.fork_from(e0)
+            for k in range(steps):
+                submit(warmup + k)
+            runner.join_into(cur)
+            e1.record(cur)
+            torch.cuda.synchronize()
+            wall_ = time.perf_counter() - t0
+            barrier()
+            clk = sampler.stop() if sampler else None
+            return e0.elapsed_time(e1) / 1e3, wall_, clk
+
+        dev_s, wall, clocks = timed_graph(lambda i: runner.submit(resident[i % N_INPUT_SETS]),
+                                          args.steps, args.warmup, ClockSampler(local))
+
+        def submit_e2e(i):
+            slot = runner._next
+            if i >= N_STREAMS:
+                runner.wait(slot)                     # results of the previous use of this slot are on the host
+            runner.submit(host[i % N_INPUT_SETS], to_host=True)
+
+        e2e_graph_s, _, _ = timed_graph(submit_e2e, args.steps, args.warmup)
+        graph_info = {"streams": N_STREAMS, "e2e_s": e2e_graph_s}
+
     # ---- (2) e2e: pinned host -> device -> forward -> device -> host ---------------------------
     d2h_bytes = [0]
 
@@ -284,8 +329,12 @@ def run_ours(args):
         res = [o[k].to("cpu", non_blocking=False) for k in RESULT_KEYS]
         d2h_bytes[0] = sum(r.numel() * r.element_size() for r in res)
 
-    e2e_steps, e2e_wall, _ = timed_loop(step_e2e, args.steps, args.warmup, flush, barrier)
+    e2e_steps, e2e_wall, _ = timed_loop(step_e2e, args.steps if graph_info is None else min(args.steps, 5),
+                                        args.warmup, flush, barrier)
     e2e_s = sum(e2e_steps) / 1e3
+    eager["e2e_ms_per_step"] = round(e2e_s / len(e2e_steps) * 1e3, 4)
+    if graph_info is not None:
+        e2e_s = graph_info["e2e_s"]
     h2d_bytes = host[0].numel() * host[0].element_size()
 
     # ---- (3) per-kernel event timing (separate pass so the events do not perturb (1)) ----------
@@ -339,7 +388,8 @@ def run_ours(args):
                     "traffic": None, "peak_source": peak_src,
                     "launches_per_step": d["launches"] // prof_steps,
                     "avg_launch_us": round(avg_ms * 1e3, 2), "algo_bytes_per_launch": int(avg_bytes),
-                    "share_of_step": round(d["ms"] / prof_steps / (dev_s / args.steps * 1e3), 4)}
+                    "share_of_step": round(d["ms"] / prof_steps / eager["ms_per_step"], 4),
+                    "share_of": "eager single-stream step (kernels of different batches overlap in graph mode)"}
     fps = agg.get("spc_furthest_point_sampling")
     latency_bound = None
     if fps:
@@ -361,7 +411,10 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
                        "input_feature_dim": FEATURE_DIM, "weights": "random init (seed 0), eval mode",
                        "precision": "shared-MLP 1x1 convs in bf16 on tcgen05 with fp32 accumulation; point ops fp32/int32",
-                       "l2": "256 MiB L2 flush between timed steps; %d rotating input batches" % N_INPUT_SETS,
+                       "l2": ("inputs larger than L2: %d distinct batches (%.0f MB) rotated; " % (N_INPUT_SETS, N_INPUT_SETS * 5.12)) +
+                             ("CUDA-graph replay on %d streams (batches overlap, no flush possible between them)" % N_STREAMS
+                              if graph_info is not None else "256 MiB L2 flush between timed steps"),
+                       "execution": ("cuda-graph x %d streams" % N_STREAMS) if graph_info is not None else "eager, 1 stream",
                        "parallelism": "scenes sharded by batch, %d rank(s), no collective" % world},
             "e2e": {"value": round(total_scenes / e2e_s, 3), "unit": "scenes/s",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes[0]),
@@ -370,6 +423,7 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "roofline": roofline, "latency_bound": latency_bound, "ops": ops,
             "kernel_ms_per_step": round(step_ms_kernels, 4),
+            "eager": eager,
             "cpu_baseline": cpu_base, "clocks": clocks,
             "wall_s_timed_region": round(wall, 4),
         }
@@ -572,8 +626,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=N_STREAMS, help="graph replay streams (batches in flight)")
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: CUDA-graph replay on %d streams (headline); eager: plain launches" % N_STREAMS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global N_STREAMS
+    N_STREAMS = max(1, args.streams)
     if args.impl == "reference":
         run_reference(args)
     else:
