@@ -54,6 +54,10 @@ int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint, int3
  * rounds, all others run the normal kernel.  Results are identical to spc_furthest_point_sampling
  * in every case; the hint only affects speed. */
 size_t spc_fps_workspace_bytes(int B, int N, int npoint);
+/* Tuning knob, process-wide: CTAs per scene cluster for large clouds (0 = automatic = 8).  Does not
+ * change results.  4 halves the SM-time per call (throughput with several batches in flight), 8
+ * minimises the latency of a single call. */
+int spc_set_fps_cluster(int cluster_ctas);
 int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                    float *new_xyz, int hint_ordered, void *workspace,
                                    size_t workspace_bytes, void *stream);

@@ -431,6 +431,20 @@ using namespace spc;
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
                     int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_);
 
+// process-wide tuning knob (0 = automatic).  8-CTA clusters minimise the latency of one call;
+// 4-CTA clusters cost ~15 % more time per call but half the SM-time, which is what matters when
+// several batches are in flight on different streams (spacap3d_b200/pipeline.py).
+static int g_fps_cluster = 0;
+extern "C" int spc_set_fps_cluster(int cluster_ctas) {
+  if (cluster_ctas != 0 && cluster_ctas != 1 && cluster_ctas != 2 && cluster_ctas != 4 && cluster_ctas != 8 &&
+      cluster_ctas != 16) {
+    set_error("spc_set_fps_cluster: %d is not one of 0,1,2,4,8,16", cluster_ctas);
+    return SPC_ERR_INVALID_ARG;
+  }
+  g_fps_cluster = cluster_ctas;
+  return SPC_OK;
+}
+
 extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
   (void)N;
   return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B) * 4;
@@ -493,6 +507,7 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   if (cached_max8 < 0) cached_max8 = max_active_clusters<10, 512, true>(8);
   int C = 8;
   if (cached_max8 > 0 && cached_max8 < B) C = (B * 4 <= kNumSMs) ? 4 : 2;
+  if (g_fps_cluster) C = g_fps_cluster;
   if (const char *e = getenv("SPC_FPS_CLUSTER")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
   int need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512));
   while (need > 32 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }

@@ -19,8 +19,13 @@ class GraphedDetector:
     replays the graph and (optionally) copies the requested outputs to pinned host buffers; it
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
-    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3):
+    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None):
         assert example.is_cuda
+        # with >= 3 batches in flight the SM-time of FPS matters more than its latency: 4-CTA clusters
+        if fps_cluster is None:
+            fps_cluster = 4 if n_streams >= 3 else 0
+        from . import _lib
+        _lib.call("spc_set_fps_cluster", int(fps_cluster))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)
