@@ -158,15 +158,15 @@ ALGO_BYTES = {
     "spc_three_nn": lambda a: a[2] * (12 * (a[3] + a[4]) + 24 * a[3]),
     "spc_furthest_point_sampling": lambda a: a[1] * (12 * a[2] + 4 * a[3] + (12 * a[3] if a[5] else 0)),
     # fused SA fwd = 12n + 4*C*n + 4*np*ns + 4*C_out*np per scene (C = table width actually read)
-    "spc_sa_fused_forward": lambda a: a[14] * (12 * a[15] + 4 * (a[18] if a[3] else a[8]) * a[15]
-                                               + 4 * a[16] * a[17] + 4 * a[20] * a[16]),
+    "spc_sa_fused_forward": lambda a: a[13] * (12 * a[14] + (2 * a[17] if a[3] else 4 * a[7]) * a[14]
+                                               + 4 * a[15] * a[16] + 4 * a[19] * a[15]),
 }
 # algorithmic FLOPs (2 * sum_l C_l*C_{l+1} * np*ns) of the MLP a fused launch replaces;
 # C_0 = 3 + input channels is not known to the projected form, so only layers 1,2 (the tcgen05
 # part) plus the in-line layer 0 are counted -- a lower bound on the replaced work
 ALGO_FLOPS = {
-    "spc_sa_fused_forward": lambda a: 2 * a[14] * a[16] * a[17] * (
-        a[18] * a[19] + a[19] * a[20] + (0 if a[3] else (3 + a[8]) * a[18])),
+    "spc_sa_fused_forward": lambda a: 2 * a[13] * a[15] * a[16] * (
+        a[17] * a[18] + a[18] * a[19] + (3 if a[3] else 3 + a[7]) * a[17]),
 }
 ROOFLINE_BOUNDED = ("spc_group_points", "spc_three_interpolate", "spc_gather_points", "spc_sa_fused_forward")
 

@@ -120,21 +120,23 @@ int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const 
  * 3 x [1x1 conv, BN, ReLU]) and pointnet2_modules.py:256-271 (max-pool over nsample)).
  *   xyz (B,n,3), new_xyz (B,npoint,3), idx (B,npoint,nsample) from spc_ball_query.
  *   Layer 0, one of two forms (BatchNorm folded into weights/bias by the caller):
- *     projected: G (B,n,C1) = per-point conv0 response, Hc (B,npoint,C1) = per-centre bias;
- *                h1 = relu(G[idx] + Hc[centre]);  feat/W0/b0 unused (NULL)
- *     inline   : G == NULL; feat (B,Cf,n) raw features (Cf <= 16, may be NULL when Cf == 0),
+ *     in-line  : G_bf16 == NULL; feat (B,Cf,n) raw features (Cf <= 16, NULL when Cf == 0),
  *                W0 (C1,3+Cf), b0 (C1);  h1 = relu(W0 . [(p-c)/radius, f] + b0)
+ *     projected: G_bf16 (B,n,C1) BF16 = W0[:,3:] . f per POINT (one plain GEMM by the caller, conv0 is
+ *                linear), Cf == 0, W0 (C1,3) = the xyz columns, b0 (C1);
+ *                h1 = relu(G[idx] + W0 . (p-c)/radius + b0), the xyz term evaluated in fp32 here
  *   Layers 1,2: W1 (C2,C1), W2 (C3,C2) row-major BF16 (device pointers to 16-bit data), b1, b2 f32;
  *   run on tcgen05 tensor cores, fp32 accumulation in TMEM.
- *   out (B,C3,npoint) = max over nsample of relu(layer2).
+ *   out (B,C3,npoint) f32 = max over nsample of relu(layer2); out_pm_bf16 (optional, may be NULL):
+ *   the same values as (B,npoint,C3) BF16, point-major (input of the next layer's projection GEMM).
  * Returns SPC_ERR_UNSUPPORTED (nothing launched) for shapes without a kernel: supported are
  * (C1,C2,C3) in {(64,64,128),(128,128,128),(128,128,256)}, nsample in {16,32,64},
  * npoint*nsample % 128 == 0. */
 int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *idx,
-                         const float *G, const float *Hc, const float *feat, const float *W0,
-                         const float *b0, int Cf, float radius, const void *W1_bf16,
-                         const float *b1, const void *W2_bf16, const float *b2, int B, int n,
-                         int npoint, int nsample, int C1, int C2, int C3, float *out, void *stream);
+                         const void *G_bf16, const float *feat, const float *W0, const float *b0,
+                         int Cf, float radius, const void *W1_bf16, const float *b1,
+                         const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample,
+                         int C1, int C2, int C3, float *out, void *out_pm_bf16, void *stream);
 
 #ifdef __cplusplus
 }

@@ -192,46 +192,48 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     return out
 
 
-def sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, *, G=None, Hc=None, feat=None, W0=None,
-                     b0=None, radius=1.0):
+def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=None, radius=1.0,
+                     want_point_major=False):
     """Fused set-abstraction forward (eval): gather + layer 0 + two tcgen05 1x1 convs + max-pool.
-    See spc_sa_fused_forward in include/spacap3d_ops.h.  Raises _lib.SpcUnsupported when the
-    library has no kernel for the shape (caller then uses the unfused CUDA ops)."""
+    See spc_sa_fused_forward in include/spacap3d_ops.h.
+      in-line form   : G is None, feat (B,Cf,n) or None, W0 (C1,3+Cf)
+      projected form : G (B,n,C1) bf16 = per-point projection of the features, W0 (C1,3)
+    Returns out (B,C3,npoint) f32, and also the point-major bf16 copy (B,npoint,C3) when
+    want_point_major.  Raises _lib.SpcUnsupported when the library has no kernel for the shape
+    (the caller then uses the unfused CUDA ops)."""
     _check(xyz, "xyz", torch.float32)
     _check(new_xyz, "new_xyz", torch.float32)
     _check(idx, "idx", torch.int32)
+    _check(W0, "W0", torch.float32)
+    _check(b0, "b0", torch.float32)
     _check(W1, "W1", torch.bfloat16)
     _check(W2, "W2", torch.bfloat16)
     _check(b1, "b1", torch.float32)
     _check(b2, "b2", torch.float32)
-    _same_device(xyz, new_xyz, idx, W1, b1, W2, b2)
+    _same_device(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2)
     B, n, _ = xyz.shape
     _, npoint, nsample = idx.shape
     C2, C1 = W1.shape
     C3 = W2.shape[0]
-    assert W2.shape[1] == C2 and b1.numel() == C2 and b2.numel() == C3
+    assert W2.shape[1] == C2 and b1.numel() == C2 and b2.numel() == C3 and b0.numel() == C1
+    Cf, pG, pfeat = 0, None, None
     if G is not None:
-        _check(G, "G", torch.float32)
-        _check(Hc, "Hc", torch.float32)
-        _same_device(xyz, G, Hc)
-        assert G.shape == (B, n, C1) and Hc.shape == (B, npoint, C1)
-        Cf, pG, pHc, pfeat, pW0, pb0 = 0, G.data_ptr(), Hc.data_ptr(), None, None, None
+        _check(G, "G", torch.bfloat16)
+        _same_device(xyz, G)
+        assert G.shape == (B, n, C1) and W0.shape == (C1, 3)
+        pG = G.data_ptr()
     else:
-        _check(W0, "W0", torch.float32)
-        _check(b0, "b0", torch.float32)
-        Cf = 0
-        pfeat = None
         if feat is not None:
             _check(feat, "feat", torch.float32)
             _same_device(xyz, feat)
             Cf = feat.shape[1]
             pfeat = feat.data_ptr()
-        assert W0.shape == (C1, 3 + Cf) and b0.numel() == C1
-        pG, pHc, pW0, pb0 = None, None, W0.data_ptr(), b0.data_ptr()
+        assert W0.shape == (C1, 3 + Cf)
     out = torch.empty((B, C3, npoint), dtype=torch.float32, device=xyz.device)
+    out_pm = torch.empty((B, npoint, C3), dtype=torch.bfloat16, device=xyz.device) if want_point_major else None
     with torch.cuda.device(xyz.device):
         _lib.call("spc_sa_fused_forward", xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
-                  pG, pHc, pfeat, pW0, pb0, int(Cf), float(radius), W1.data_ptr(), b1.data_ptr(),
-                  W2.data_ptr(), b2.data_ptr(), B, n, npoint, nsample, C1, C2, C3,
-                  out.data_ptr(), _stream())
-    return out
+                  pG, pfeat, W0.data_ptr(), b0.data_ptr(), int(Cf), float(radius), W1.data_ptr(),
+                  b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), B, n, npoint, nsample, C1, C2, C3,
+                  out.data_ptr(), out_pm.data_ptr() if out_pm is not None else None, _stream())
+    return (out, out_pm) if want_point_major else out

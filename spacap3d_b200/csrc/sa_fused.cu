@@ -1,6 +1,7 @@
 // sa_fused.cu -- fused set-abstraction forward (eval mode): grouping + relative-xyz
 // normalisation + shared MLP (3 x [1x1 conv + folded BN + ReLU]) + max-pool over nsample in ONE
-// kernel, the two wide 1x1 convs on tcgen05 tensor cores with TMEM accumulators (sm_100a).
+// warp-specialised kernel, the two wide 1x1 convs on tcgen05 tensor cores with TMEM accumulators
+// (sm_100a).
 //
 // Replaces, for PointnetSAModuleVotes.forward in eval mode (reference pointnet2_modules.py:244-271):
 //   QueryAndGroup's two group_points launches + sub + div + cat (pointnet2_utils.py:351-362),
@@ -10,11 +11,12 @@
 //
 // Algorithm (per tile of 128 rows, a row = one (centre, neighbour) pair):
 //   layer 0  h1 = relu(W0' . [ (p_i - c_j)/r , f_i ] + b0)         CUDA cores, in the gather stage
-//            MODE_PROJ: the feature part of conv0 only depends on the POINT, not on the pair, so
-//            it is hoisted out of the grouping: G[i] = W0' . [p_i/r, f_i] is precomputed per point
-//            (npoint*nsample/n = 4..16x fewer MACs) and Hc[j] = b0 - W0x' . c_j/r per centre; the
-//            stage then only gathers:  h1 = relu(G[idx] + Hc[j]).
-//            MODE_INLINE (few input channels, SA1): evaluated directly from xyz and raw features.
+//            in-line form (few input channels, SA1): evaluated directly from xyz and raw features.
+//            projected form: conv0 is linear and its feature part only depends on the POINT, not on
+//            the pair, so it is hoisted out of the grouping: G[i] = W0f' . f_i is one plain GEMM per
+//            layer over the n points (npoint*nsample/n = 4..16x fewer MACs) and the kernel evaluates
+//            h1 = relu(G[idx] + W0x' . (p_i - c_j)/r + b0) -- the xyz term stays in fp32 inside the
+//            kernel (it is a difference of nearby points; G is bf16).
 //   layer 1  D1[128 rows x C2]  = H1[128 x C1] . W1'^T             tcgen05.mma, M=128, N=C2
 //            h2 = relu(D1 + b1) -> bf16 -> shared memory (thread per row, TMEM lane = row)
 //   layer 2  D2[C3 x 128 rows]  = W2'[C3 x C2] . H2^T              tcgen05.mma, TRANSPOSED so that a
@@ -23,10 +25,11 @@
 //   out[b, c, j] = relu(max_k D2[c, j*ns+k] + b2[c])   (ReLU and +b commute with max)
 // BN (eval) is folded on the host: W' = diag(gamma/sqrt(var+eps)) W, b = beta - mean*scale.
 //
-// Shared-memory operand layout: canonical UMMA K-major, no swizzle: 8-element (16 B) chunks,
-// element (row, k) at (k/8)*ROWS*16 + row*16 + (k%8)*2 bytes, i.e. core matrices of 8 rows x 16 B
-// are contiguous (SBO = 128 B) and K-chunks are ROWS*16 B apart (LBO).  Both the gather stage and
-// the epilogue write one 16-byte chunk per lane with lane = row, which is bank-conflict free.
+// Shared-memory operands: canonical UMMA K-major layout with 128-byte swizzle (a row = 128
+// contiguous bytes per 64-element K atom, chunk c of row r at position c ^ (r & 7)).  With it both
+// a warp writing one whole row (row-wise gather) and 8 lanes writing the same chunk of 8
+// consecutive rows (epilogue, lane = row) are bank-conflict free, and no TMA descriptor is needed
+// for gathered data.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -127,25 +130,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) leading (K-direction) byte offset >> 4 |
-//   [32,46) stride (8-row group) byte offset >> 4 | [46,48) version = 1 | [61,64) layout = 0
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                   uint32_t sbo_bytes, int swap = 0) {
-  if (swap) { const uint32_t t = lbo_bytes; lbo_bytes = sbo_bytes; sbo_bytes = t; }
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Same descriptor for the 128-byte-swizzle K-major layout (layout type 2): a row is 128 contiguous
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout: [0,14) start address >> 4,
+// [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4, [46,48) version = 1,
+// [61,64) layout type) for the 128-byte-swizzle K-major layout (type 2): a row is 128 contiguous
 // bytes (64 bf16), 8-row groups are 1024 B apart (SBO), the 16-byte chunk c of row r sits at chunk
 // position c ^ (r & 7) (Swizzle<3,4,3>); K beyond 64 elements continues in the next "K atom",
 // rows*128 bytes further.  The leading-byte-offset field is unused for swizzled K-major (= 1).
@@ -167,6 +159,14 @@ __device__ __forceinline__ uint32_t sw128_kstep(int kk, int rows) {
   return (uint32_t)((kk >> 2) * rows * 128 + (kk & 3) * 32);
 }
 
+// relu + round-to-nearest bf16 conversion + packing of two floats in ONE instruction
+// (cvt.rn.relu.bf16x2.f32: first source -> upper half, second source -> lower half)
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
@@ -177,12 +177,9 @@ struct SaFusedParams {
   const float *xyz;       // (B,n,3)
   const float *new_xyz;   // (B,np,3)
   const int32_t *idx;     // (B,np,ns)
-  // MODE_PROJ
-  const float *G;         // (B,n,C1)  per-point projection (BN scale folded)
-  const float *Hc;        // (B,np,C1) per-centre bias
-  // MODE_INLINE
-  const float *feat;      // (B,Cf,n) or nullptr
-  const float *W0;        // (C1, 3+Cf) folded, fp32
+  const __nv_bfloat16 *G; // projected form: (B,n,C1) per-point feature projection (BN scale folded)
+  const float *feat;      // in-line form: (B,Cf,n) raw features or nullptr
+  const float *W0;        // (C1, 3+Cf) folded, fp32; projected form: Cf = 0, i.e. the xyz columns only
   const float *b0;        // (C1)
   int Cf;
   float radius;           // divide relative xyz by this (1.0 when normalize_xyz is off)
@@ -191,74 +188,17 @@ struct SaFusedParams {
   const __nv_bfloat16 *W2;  // (C3,C2)
   const float *b2;          // (C3)
   float *out;             // (B,C3,np)
+  __nv_bfloat16 *out_pm;  // optional (B,np,C3): the same result point-major in bf16 (next layer's GEMM input)
   int B, n, np, ns;
   int num_tiles;          // B*np*ns/128
-  int desc_swap;          // debug (env SPC_SA_DESC_SWAP=1): swap LBO/SBO roles in the descriptors
 };
 
-constexpr int SA_THREADS = 256;
 constexpr int SA_ROWS = 128;        // rows (centre,neighbour pairs) per tile
 constexpr int SA_MAX_K0 = 3 + 16;   // MODE_INLINE supports up to 16 raw feature channels
 constexpr int SA_W0_STRIDE = 20;    // floats per channel row of the inline layer-0 weights (K0+1 padded)
 
-template <int C1, int C2, int C3>
-struct SaSmem {
-  static constexpr int W1_BYTES = C2 * C1 * 2;
-  static constexpr int W2_BYTES = C3 * C2 * 2;
-  static constexpr int H1_BYTES = SA_ROWS * C1 * 2;
-  static constexpr int H2_BYTES = SA_ROWS * C2 * 2;
-  static constexpr int OFF_W1 = 0;
-  static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-  static constexpr int OFF_H1 = OFF_W2 + W2_BYTES;
-  static constexpr int OFF_H2 = OFF_H1 + H1_BYTES;
-  static constexpr int OFF_B1 = OFF_H2 + H2_BYTES;          // C2 floats
-  static constexpr int OFF_W0 = OFF_B1 + C2 * 4;            // C1*(SA_MAX_K0+1) floats (inline mode)
-  static constexpr int TOTAL_PROJ = OFF_W0;
-  static constexpr int TOTAL_INLINE = OFF_W0 + C1 * SA_W0_STRIDE * 4;
-  static constexpr int TMEM_COLS_USED = C2 + (C3 / 128) * SA_ROWS;
-  static constexpr int TMEM_COLS = TMEM_COLS_USED <= 32 ? 32 : TMEM_COLS_USED <= 64 ? 64
-                                   : TMEM_COLS_USED <= 128 ? 128 : TMEM_COLS_USED <= 256 ? 256 : 512;
-};
-
-// copy a row-major bf16 matrix [rows x K] from global into the blocked K-major smem layout
-__device__ __forceinline__ void load_weights_blocked(uint8_t *dst, const __nv_bfloat16 *src, int rows,
-                                                     int K, int tid) {
-  const int chunks = K / 8;
-  for (int e = tid; e < rows * chunks; e += SA_THREADS) {
-    const int r = e / chunks, kc = e - r * chunks;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * K + kc * 8));
-    *reinterpret_cast<uint4 *>(dst + (size_t)kc * rows * 16 + r * 16) = v;
-  }
-}
-
-// Gather stage + layer 0 for ONE row of a tile: writes chunks [kc0, kc0+NKC) of row r of H1
-// (bf16, blocked K-major).  Shared by the serial and the pipelined kernel.  `i` is the
-// neighbour index idx[R] (loaded by the caller so that it can be prefetched a tile ahead).
-template <int C1, int NKC>
-__device__ __forceinline__ void sa_produce_proj(const SaFusedParams &p, int b, int j, int i, int r, int kc0,
-                                                uint8_t *sH1) {
-  const float4 *g = reinterpret_cast<const float4 *>(p.G + ((size_t)b * p.n + i) * C1) + 2 * kc0;
-  const float4 *h = reinterpret_cast<const float4 *>(p.Hc + ((size_t)b * p.np + j) * C1) + 2 * kc0;
-  // all gather loads of this thread are issued before the first use: the stage is bound by L2
-  // latency/bandwidth, so memory-level parallelism is what matters
-  float4 gv[2 * NKC];
-#pragma unroll
-  for (int c = 0; c < 2 * NKC; ++c) gv[c] = __ldg(g + c);
-#pragma unroll
-  for (int kc = 0; kc < NKC; ++kc) {
-    const float4 h0 = __ldg(h + 2 * kc), h1 = __ldg(h + 2 * kc + 1);     // per-centre row: L1 hits
-    const float4 g0 = gv[2 * kc], g1 = gv[2 * kc + 1];
-    uint4 o;
-    o.x = pack_bf16x2(fmaxf(g0.x + h0.x, 0.f), fmaxf(g0.y + h0.y, 0.f));
-    o.y = pack_bf16x2(fmaxf(g0.z + h0.z, 0.f), fmaxf(g0.w + h0.w, 0.f));
-    o.z = pack_bf16x2(fmaxf(g1.x + h1.x, 0.f), fmaxf(g1.y + h1.y, 0.f));
-    o.w = pack_bf16x2(fmaxf(g1.z + h1.z, 0.f), fmaxf(g1.w + h1.w, 0.f));
-    *reinterpret_cast<uint4 *>(sH1 + (size_t)(kc0 + kc) * SA_ROWS * 16 + r * 16) = o;
-  }
-}
-
 // in-line layer 0 with KQ float4 groups of inputs: in = [(p-c)/r (3), features (Cf), 1 (bias), 0...]
-template <int C1, int NKC, int KQ, bool SW = false>
+template <int C1, int NKC, int KQ>
 __device__ __forceinline__ void sa_produce_inline(const SaFusedParams &p, int b, int j, int i, int r, int kc0,
                                                   uint8_t *sH1, const float *sW0, int K0) {
   float in[4 * KQ];
@@ -287,242 +227,77 @@ __device__ __forceinline__ void sa_produce_inline(const SaFusedParams &p, int b,
         a = fmaf(wv.z, in[4 * g4 + 2], a);
         a = fmaf(wv.w, in[4 * g4 + 3], a);
       }
-      acc[c] = fmaxf(a, 0.f);
+      acc[c] = a;
     }
     uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]);
-    o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]);
-    o.w = pack_bf16x2(acc[6], acc[7]);
-    *reinterpret_cast<uint4 *>(sH1 + (SW ? sw128_off(r, kc, SA_ROWS) : (uint32_t)(kc * SA_ROWS * 16 + r * 16))) = o;
+    o.x = pack_relu_bf16x2(acc[0], acc[1]);
+    o.y = pack_relu_bf16x2(acc[2], acc[3]);
+    o.z = pack_relu_bf16x2(acc[4], acc[5]);
+    o.w = pack_relu_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = o;
   }
 }
 
-// Projected layer 0 for the pipelined kernel: ONE WARP PER ROW so that the gather of a 4*C1-byte
-// G row is a single coalesced request (4 L1 wavefronts instead of 32 with lane = row), 16 rows in
-// flight per warp; the 8-byte bf16 results go to the 128B-swizzled H1, where a row is one
-// contiguous 128-byte line per K atom => conflict-free stores.
+// Projected layer 0: ONE WARP PER ROW PAIR so that the gather of a 2*C1-byte G row (bf16) is a
+// coalesced request (2 L1 wavefronts per row instead of 16+ with lane = row), 16 rows in flight per
+// warp.  Lane = 8 consecutive channels of one row: one 16-byte load, 8 x (3 FMA + add + relu) with
+// this lane's xyz weights / bias in registers, one 16-byte store into the swizzled H1.
 template <int C1>
 __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, int tile, int warp, int lane,
-                                                        int my_idx, uint8_t *sH1, int rows_per_scene) {
-  constexpr int LPR = C1 / 4;                 // lanes per row (float4 each)
+                                                        int my_idx, const float (&wx)[8][3], const float (&wb)[8],
+                                                        uint8_t *sH1, int rows_per_scene) {
+  constexpr int LPR = C1 / 8;                 // lanes per row (8 bf16 = 16 bytes each)
   constexpr int RPI = 32 / LPR;               // rows per warp-wide load
   constexpr int NPASS = 16 / RPI;             // a warp owns 16 rows of the tile
-  const int c4 = lane % LPR;
+  const int kc = lane % LPR;
   const int sub = lane / LPR;
   const long long R0 = (long long)tile * SA_ROWS + warp * 16;
   const int b = (int)(R0 / rows_per_scene);
   const int j = (int)(R0 - (long long)b * rows_per_scene) / p.ns;      // the 16 rows share one centre (ns >= 16)
-  const float *Gb = p.G + (size_t)b * p.n * C1 + 4 * c4;
-  float4 g[NPASS];
+  const __nv_bfloat16 *Gb = p.G + (size_t)b * p.n * C1 + 8 * kc;
+  const float *Pb = p.xyz + (size_t)b * p.n * 3;
+  const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
+  const float cx = __ldg(cc), cy = __ldg(cc + 1), cz = __ldg(cc + 2);
+  const float inv_r = 1.0f / p.radius;
+  // two batches of NPASS/2 rows: enough loads in flight to cover the L2 latency without
+  // exceeding the 96-register budget of the 17-warp CTA
+  constexpr int HB = NPASS / 2 > 0 ? NPASS / 2 : 1;
 #pragma unroll
-  for (int t = 0; t < NPASS; ++t) {
-    const int i = __shfl_sync(0xffffffffu, my_idx, t * RPI + sub);    // lanes 0..15 hold idx of the 16 rows
-    g[t] = __ldg(reinterpret_cast<const float4 *>(Gb + (size_t)i * C1));
-  }
-  const float4 h = __ldg(reinterpret_cast<const float4 *>(p.Hc + ((size_t)b * p.np + j) * C1 + 4 * c4));
+  for (int t0 = 0; t0 < NPASS; t0 += HB) {
+    uint4 g[HB];
+    float rx[HB], ry[HB], rz[HB];
 #pragma unroll
-  for (int t = 0; t < NPASS; ++t) {
-    const int r = warp * 16 + t * RPI + sub;
-    uint2 o;
-    o.x = pack_bf16x2(fmaxf(g[t].x + h.x, 0.f), fmaxf(g[t].y + h.y, 0.f));
-    o.y = pack_bf16x2(fmaxf(g[t].z + h.z, 0.f), fmaxf(g[t].w + h.w, 0.f));
-    *reinterpret_cast<uint2 *>(sH1 + sw128_off(r, c4 >> 1, SA_ROWS) + (c4 & 1) * 8) = o;
-  }
-}
-
-template <int C1, bool MODE_PROJ>
-__device__ __forceinline__ void sa_produce_rows(const SaFusedParams &p, int tile, int r, int i, int kc0,
-                                                uint8_t *sH1, const float *sW0, int K0, int rows_per_scene) {
-  constexpr int NKC = C1 / 16;                       // half of the row's 16-byte chunks
-  const long long R = (long long)tile * SA_ROWS + r; // global row
-  const int b = (int)(R / rows_per_scene);
-  const int j = (int)(R - (long long)b * rows_per_scene) / p.ns;   // centre
-  if (MODE_PROJ) {
-    sa_produce_proj<C1, NKC>(p, b, j, i, r, kc0, sH1);
-  } else {
-    switch ((K0 + 1 + 3) >> 2) {                     // float4 groups of inputs actually used (warp-uniform)
-      case 1: sa_produce_inline<C1, NKC, 1>(p, b, j, i, r, kc0, sH1, sW0, K0); break;
-      case 2: sa_produce_inline<C1, NKC, 2>(p, b, j, i, r, kc0, sH1, sW0, K0); break;
-      case 3: sa_produce_inline<C1, NKC, 3>(p, b, j, i, r, kc0, sH1, sW0, K0); break;
-      case 4: sa_produce_inline<C1, NKC, 4>(p, b, j, i, r, kc0, sH1, sW0, K0); break;
-      default: sa_produce_inline<C1, NKC, 5>(p, b, j, i, r, kc0, sH1, sW0, K0); break;
+    for (int t = 0; t < HB; ++t) {
+      const int i = __shfl_sync(0xffffffffu, my_idx, (t0 + t) * RPI + sub);   // lanes 0..15 hold idx of the 16 rows
+      g[t] = __ldg(reinterpret_cast<const uint4 *>(Gb + (size_t)i * C1));
+      // (p - c) / r as a multiplication by 1/r: this path is the bf16 one (rtol 1e-2), a 1-ulp
+      // difference to the reference's true division is irrelevant here
+      rx[t] = (__ldg(Pb + 3 * i + 0) - cx) * inv_r;
+      ry[t] = (__ldg(Pb + 3 * i + 1) - cy) * inv_r;
+      rz[t] = (__ldg(Pb + 3 * i + 2) - cz) * inv_r;
     }
-  }
-}
-
-// CTAs per SM the kernel is compiled for: two when TMEM columns and shared memory allow it (SA1
-// widths), so that one CTA's gather / epilogue overlaps the other's MMAs
-template <int C1, int C2, int C3>
-constexpr int sa_min_blocks() {
-  using L = SaSmem<C1, C2, C3>;
-  return (L::TMEM_COLS <= 256 && L::TOTAL_INLINE <= 100 * 1024) ? 2 : 1;
-}
-
-template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
-__global__ void __launch_bounds__(SA_THREADS, sa_min_blocks<C1, C2, C3>()) sa_fused_kernel(const SaFusedParams p) {
-  using L = SaSmem<C1, C2, C3>;
-  static_assert(C1 % 16 == 0 && C2 % 16 == 0 && C2 % 64 == 0 && C3 % 128 == 0, "bad widths");
-  static_assert(SA_ROWS % NS == 0 && (NS == 16 || NS == 32 || NS == 64), "bad nsample");
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_base_smem;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int q = warp & 3;          // TMEM lane quarter this warp may access
-  const int grp = warp >> 2;       // 0 or 1: which half of the column work this warp takes
-  uint8_t *sW1 = smem + L::OFF_W1, *sW2 = smem + L::OFF_W2, *sH1 = smem + L::OFF_H1,
-          *sH2 = smem + L::OFF_H2;
-  float *sB1 = reinterpret_cast<float *>(smem + L::OFF_B1);
-  float *sW0 = reinterpret_cast<float *>(smem + L::OFF_W0);   // [C1][K0+1] (last = b0), inline mode
-  const int K0 = 3 + p.Cf;
-
-  // ---- one-time setup ---------------------------------------------------------------------------
-  if (warp == 0) tmem_alloc(&tmem_base_smem, L::TMEM_COLS);
-  if (tid == 32) {
-    mbarrier_init(&mma_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  load_weights_blocked(sW1, p.W1, C2, C1, tid);
-  load_weights_blocked(sW2, p.W2, C3, C2, tid);
-  for (int e = tid; e < C2; e += SA_THREADS) sB1[e] = __ldg(p.b1 + e);
-  if (!MODE_PROJ) {
-    // row c = [w(c,0..K0-1), b0(c), 0...]: the bias rides along as the weight of a constant-1 input
-    for (int e = tid; e < C1 * SA_W0_STRIDE; e += SA_THREADS) {
-      const int c = e / SA_W0_STRIDE, k = e - c * SA_W0_STRIDE;
-      sW0[e] = k < K0 ? __ldg(p.W0 + (size_t)c * K0 + k) : (k == K0 ? __ldg(p.b0 + c) : 0.f);
-    }
-  }
-  fence_proxy_async_smem();      // weights were written through the generic proxy; UMMA reads via async proxy
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t tmem_d1 = tmem_base;             // [128 lanes x C2 cols]
-  const uint32_t tmem_d2 = tmem_base + C2;        // C3/128 blocks of [128 lanes x 128 cols]
-
-  constexpr uint32_t IDESC1 = make_idesc_bf16(128, C2);
-  constexpr uint32_t IDESC2 = make_idesc_bf16(128, SA_ROWS);
-  const uint32_t aH1 = s2u(sH1), aH2 = s2u(sH2), aW1 = s2u(sW1), aW2 = s2u(sW2);
-  unsigned phase = 0;
-  const int rows_per_scene = p.np * p.ns;
-
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-    // ================= stage 0: gather + layer 0 -> H1 (bf16, blocked K-major) ===================
-    sa_produce_rows<C1, MODE_PROJ>(p, tile, q * 32 + lane, __ldg(p.idx + (long long)tile * SA_ROWS + q * 32 + lane),
-                                   grp * (C1 / 16), sH1, sW0, K0, rows_per_scene);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ================= stage 1: D1 = H1 . W1'^T  (M=128 rows, N=C2, K=C1) =========================
-    if (tid == 0) {
-      tc_fence_after();
 #pragma unroll
-      for (int k = 0; k < C1 / 16; ++k) {
-        const uint64_t da = make_smem_desc(aH1 + k * 2 * SA_ROWS * 16, SA_ROWS * 16, 128, p.desc_swap);
-        const uint64_t db = make_smem_desc(aW1 + k * 2 * C2 * 16, C2 * 16, 128, p.desc_swap);
-        umma_bf16(tmem_d1, da, db, IDESC1, k > 0);
+    for (int t = 0; t < HB; ++t) {
+      const int r = warp * 16 + (t0 + t) * RPI + sub;
+      const uint32_t gw[4] = {g[t].x, g[t].y, g[t].z, g[t].w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int c2 = 0; c2 < 4; ++c2) {
+        const float g0 = __uint_as_float(gw[c2] << 16), g1 = __uint_as_float(gw[c2] & 0xffff0000u);   // bf16 -> f32
+        const float v0 = fmaf(wx[2 * c2][2], rz[t], fmaf(wx[2 * c2][1], ry[t], fmaf(wx[2 * c2][0], rx[t], g0 + wb[2 * c2])));
+        const float v1 = fmaf(wx[2 * c2 + 1][2], rz[t], fmaf(wx[2 * c2 + 1][1], ry[t], fmaf(wx[2 * c2 + 1][0], rx[t], g1 + wb[2 * c2 + 1])));
+        ow[c2] = pack_relu_bf16x2(v0, v1);
       }
-      umma_commit(&mma_bar);
+      *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    mbarrier_wait(&mma_bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ================= epilogue 1: h2 = relu(D1 + b1) -> H2 (thread = row) ========================
-    {
-      const int r = q * 32 + lane;
-      constexpr int COLS_PER_GRP = C2 / 2;
-#pragma unroll
-      for (int cb = 0; cb < COLS_PER_GRP; cb += 32) {
-        const int col0 = grp * COLS_PER_GRP + cb;
-        float v[32];
-        tmem_ld32(tmem_d1 + ((uint32_t)(q * 32) << 16) + col0, v);
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          const float4 ba = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8);
-          const float4 bb = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8 + 4);
-          uint4 o;
-          o.x = pack_bf16x2(fmaxf(v[c8 * 8 + 0] + ba.x, 0.f), fmaxf(v[c8 * 8 + 1] + ba.y, 0.f));
-          o.y = pack_bf16x2(fmaxf(v[c8 * 8 + 2] + ba.z, 0.f), fmaxf(v[c8 * 8 + 3] + ba.w, 0.f));
-          o.z = pack_bf16x2(fmaxf(v[c8 * 8 + 4] + bb.x, 0.f), fmaxf(v[c8 * 8 + 5] + bb.y, 0.f));
-          o.w = pack_bf16x2(fmaxf(v[c8 * 8 + 6] + bb.z, 0.f), fmaxf(v[c8 * 8 + 7] + bb.w, 0.f));
-          const int kc = (col0 >> 3) + c8;
-          *reinterpret_cast<uint4 *>(sH2 + (size_t)kc * SA_ROWS * 16 + r * 16) = o;
-        }
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ================= stage 2: D2[h] = W2'[h] . H2^T  (M=128 channels, N=128 rows, K=C2) =========
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < C3 / 128; ++h) {
-#pragma unroll
-        for (int k = 0; k < C2 / 16; ++k) {
-          const uint64_t da = make_smem_desc(aW2 + h * 128 * 16 + k * 2 * C3 * 16, C3 * 16, 128, p.desc_swap);
-          const uint64_t db = make_smem_desc(aH2 + k * 2 * SA_ROWS * 16, SA_ROWS * 16, 128, p.desc_swap);
-          umma_bf16(tmem_d2 + h * SA_ROWS, da, db, IDESC2, k > 0);
-        }
-      }
-      umma_commit(&mma_bar);
-    }
-    mbarrier_wait(&mma_bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-    // ================= epilogue 2: max over nsample, + b2, ReLU -> out (thread = channel) =========
-    {
-      constexpr int ITEMS = (C3 / 128) * 2;              // (channel block h, column half)
-      const long long R0 = (long long)tile * SA_ROWS;
-      const int b = (int)(R0 / rows_per_scene);
-      const int j0 = (int)((R0 - (long long)b * rows_per_scene) / NS);   // first centre of the tile
-#pragma unroll
-      for (int item = grp; item < ITEMS; item += 2) {
-        const int h = item >> 1, half = item & 1;
-        const int ch = h * 128 + q * 32 + lane;
-        const float bias = __ldg(p.b2 + ch);
-        float *o = p.out + ((size_t)b * C3 + ch) * p.np + j0;
-        if (NS <= 32) {
-#pragma unroll
-          for (int cb = 0; cb < 64; cb += 32) {
-            float v[32];
-            tmem_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + h * SA_ROWS + half * 64 + cb, v);
-#pragma unroll
-            for (int gI = 0; gI < 32 / NS; ++gI) {
-              float m = v[gI * NS];
-#pragma unroll
-              for (int t = 1; t < NS; ++t) m = fmaxf(m, v[gI * NS + t]);
-              o[(half * 64 + cb) / NS + gI] = fmaxf(m + bias, 0.f);
-            }
-          }
-        } else {  // NS == 64: one centre per 64-column half
-          float m = -INFINITY;
-#pragma unroll
-          for (int cb = 0; cb < 64; cb += 32) {
-            float v[32];
-            tmem_ld32(tmem_d2 + ((uint32_t)(q * 32) << 16) + h * SA_ROWS + half * 64 + cb, v);
-#pragma unroll
-            for (int t = 0; t < 32; ++t) m = fmaxf(m, v[t]);
-          }
-          o[half] = fmaxf(m + bias, 0.f);
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();   // TMEM / H1 / H2 free for the next tile
-    tc_fence_after();
   }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, L::TMEM_COLS);
 }
 
 // ================================================================================================
-// Warp-specialised, double-buffered version of the same computation.
+// Warp-specialised, double-buffered kernel.
 //
-// The serial kernel above runs gather -> MMA1 -> epilogue1 -> MMA2 -> epilogue2 back to back in
-// every CTA (tensor pipe 4-14 % active, ncu).  Here the five stages of consecutive tiles overlap:
+// A first, serial version ran gather -> MMA1 -> epilogue1 -> MMA2 -> epilogue2 back to back in every
+// CTA (tensor pipe 4-14 % active, ncu).  Here the five stages of consecutive tiles overlap:
 //   warps 0-7   PRODUCERS   gather + layer 0            -> H1[s]      (s = tile parity)
 //   warp  16    MMA ISSUER  one thread: MMA1(k) then MMA2(k-1)        (tcgen05, D in TMEM)
 //   warps 8-11  EPILOGUE 1  D1[s] -> relu(+b1) -> bf16  -> H2[s]
@@ -622,7 +397,18 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
   if (warp < SAP_PROD_WARPS) {
     // =============================== PRODUCERS ===================================================
     if (MODE_PROJ) {
-      // warp per row group: lanes 0..15 carry the neighbour indices of the warp's 16 rows
+      // warp per row group: lanes 0..15 carry the neighbour indices of the warp's 16 rows; every
+      // lane keeps the xyz weights and bias of its 8 channels in registers
+      constexpr int LPR = C1 / 8;
+      float wx[8][3], wb[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ch = (lane % LPR) * 8 + c;
+        wx[c][0] = __ldg(p.W0 + ch * 3 + 0);
+        wx[c][1] = __ldg(p.W0 + ch * 3 + 1);
+        wx[c][2] = __ldg(p.W0 + ch * 3 + 2);
+        wb[c] = __ldg(p.b0 + ch);
+      }
       auto load_idx = [&](int tile) {
         return lane < 16 ? __ldg(p.idx + (long long)tile * SA_ROWS + warp * 16 + lane) : 0;
       };
@@ -633,7 +419,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         const int my_idx = i_next;
         if (k + 1 < nt) i_next = load_idx(tile + (int)gridDim.x);              // a tile ahead
         mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);           // MMA1(k-2) has consumed H1[s]
-        sa_produce_proj_rowwise<C1>(p, tile, warp, lane, my_idx, sH1 + s * L::H1_BYTES, rows_per_scene);
+        sa_produce_proj_rowwise<C1>(p, tile, warp, lane, my_idx, wx, wb, sH1 + s * L::H1_BYTES, rows_per_scene);
         fence_proxy_async_smem();
         mbarrier_arrive(&h1_full[s]);
       }
@@ -653,11 +439,11 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
         uint8_t *h1 = sH1 + s * L::H1_BYTES;
         switch ((K0 + 1 + 3) >> 2) {
-          case 1: sa_produce_inline<C1, NKC, 1, true>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 2: sa_produce_inline<C1, NKC, 2, true>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 3: sa_produce_inline<C1, NKC, 3, true>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 4: sa_produce_inline<C1, NKC, 4, true>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          default: sa_produce_inline<C1, NKC, 5, true>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+          case 1: sa_produce_inline<C1, NKC, 1>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+          case 2: sa_produce_inline<C1, NKC, 2>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+          case 3: sa_produce_inline<C1, NKC, 3>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+          case 4: sa_produce_inline<C1, NKC, 4>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+          default: sa_produce_inline<C1, NKC, 5>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
         }
         fence_proxy_async_smem();
         mbarrier_arrive(&h1_full[s]);
@@ -724,10 +510,10 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
           const float4 ba = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8);
           const float4 bb = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8 + 4);
           uint4 o;
-          o.x = pack_bf16x2(fmaxf(v[c8 * 8 + 0] + ba.x, 0.f), fmaxf(v[c8 * 8 + 1] + ba.y, 0.f));
-          o.y = pack_bf16x2(fmaxf(v[c8 * 8 + 2] + ba.z, 0.f), fmaxf(v[c8 * 8 + 3] + ba.w, 0.f));
-          o.z = pack_bf16x2(fmaxf(v[c8 * 8 + 4] + bb.x, 0.f), fmaxf(v[c8 * 8 + 5] + bb.y, 0.f));
-          o.w = pack_bf16x2(fmaxf(v[c8 * 8 + 6] + bb.z, 0.f), fmaxf(v[c8 * 8 + 7] + bb.w, 0.f));
+          o.x = pack_relu_bf16x2(v[c8 * 8 + 0] + ba.x, v[c8 * 8 + 1] + ba.y);
+          o.y = pack_relu_bf16x2(v[c8 * 8 + 2] + ba.z, v[c8 * 8 + 3] + ba.w);
+          o.z = pack_relu_bf16x2(v[c8 * 8 + 4] + bb.x, v[c8 * 8 + 5] + bb.y);
+          o.w = pack_relu_bf16x2(v[c8 * 8 + 6] + bb.z, v[c8 * 8 + 7] + bb.w);
           *reinterpret_cast<uint4 *>(h2 + sw128_off(r, (col0 >> 3) + c8, SA_ROWS)) = o;
         }
       }
@@ -751,6 +537,8 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         const int ch = h * 128 + q * 32 + lane;
         const float bias = __ldg(p.b2 + ch);
         float *o = p.out + ((size_t)b * C3 + ch) * p.np + j0;
+        // optional point-major bf16 copy: lanes = consecutive channels => 64-byte coalesced stores
+        __nv_bfloat16 *opm = p.out_pm ? p.out_pm + ((size_t)b * p.np + j0) * C3 + ch : nullptr;
         float m64 = -INFINITY;
 #pragma unroll
         for (int cb = 0; cb < SA_ROWS; cb += 32) {
@@ -762,12 +550,19 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
               float m = v[gI * NS];
 #pragma unroll
               for (int t = 1; t < NS; ++t) m = fmaxf(m, v[gI * NS + t]);
-              o[cb / NS + gI] = fmaxf(m + bias, 0.f);
+              const float res = fmaxf(m + bias, 0.f);
+              o[cb / NS + gI] = res;
+              if (opm) opm[(size_t)(cb / NS + gI) * C3] = __float2bfloat16_rn(res);
             }
           } else {                                               // NS == 64: two 32-column loads per centre
 #pragma unroll
             for (int t = 0; t < 32; ++t) m64 = fmaxf(m64, v[t]);
-            if ((cb & 32) != 0) { o[cb / 64] = fmaxf(m64 + bias, 0.f); m64 = -INFINITY; }
+            if ((cb & 32) != 0) {
+              const float res = fmaxf(m64 + bias, 0.f);
+              o[cb / 64] = res;
+              if (opm) opm[(size_t)(cb / 64) * C3] = __float2bfloat16_rn(res);
+              m64 = -INFINITY;
+            }
           }
         }
         tc_fence_before();
@@ -796,42 +591,22 @@ static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   return SPC_OK;
 }
 
-template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
-static int launch_sa(const SaFusedParams &p, cudaStream_t stream) {
-  using L = SaSmem<C1, C2, C3>;
-  auto kern = sa_fused_kernel<C1, C2, C3, NS, MODE_PROJ>;
-  const int smem = MODE_PROJ ? L::TOTAL_PROJ : L::TOTAL_INLINE;
-  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                cudaSharedmemCarveoutMaxShared));
-  // CTAs per SM are bounded by TMEM columns (512 per SM) and shared memory
-  int per_sm = 512 / L::TMEM_COLS;
-  const int by_smem = (227 * 1024) / (smem + 2048);
-  if (per_sm > by_smem) per_sm = by_smem;
-  if (per_sm > sa_min_blocks<C1, C2, C3>()) per_sm = sa_min_blocks<C1, C2, C3>();
-  if (per_sm < 1) per_sm = 1;
-  int grid = kNumSMs * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<grid, SA_THREADS, smem, stream>>>(p);
-  SPC_LAUNCH_CHECK("sa_fused_kernel");
-  return SPC_OK;
-}
-
 }  // namespace spc
 
 using namespace spc;
 
 extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *idx,
-                                    const float *G, const float *Hc, const float *feat,
-                                    const float *W0, const float *b0, int Cf, float radius,
-                                    const void *W1_bf16, const float *b1, const void *W2_bf16,
-                                    const float *b2, int B, int n, int npoint, int nsample, int C1,
-                                    int C2, int C3, float *out, void *stream_) {
+                                    const void *G_bf16, const float *feat, const float *W0,
+                                    const float *b0, int Cf, float radius, const void *W1_bf16,
+                                    const float *b1, const void *W2_bf16, const float *b2, int B, int n,
+                                    int npoint, int nsample, int C1, int C2, int C3, float *out,
+                                    void *out_pm_bf16, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && n >= 1 && npoint >= 0 && nsample >= 1, "sa_fused: bad sizes");
   if (B == 0 || npoint == 0) return SPC_OK;
-  SPC_CHECK_ARG(xyz && new_xyz && idx && W1_bf16 && b1 && W2_bf16 && b2 && out, "sa_fused: null pointer");
-  const bool proj = G != nullptr;
-  SPC_CHECK_ARG(proj ? (Hc != nullptr) : (W0 && b0 && (feat || Cf == 0)), "sa_fused: missing layer-0 operands");
+  SPC_CHECK_ARG(xyz && new_xyz && idx && W0 && b0 && W1_bf16 && b1 && W2_bf16 && b2 && out,
+                "sa_fused: null pointer");
+  const bool proj = G_bf16 != nullptr;
+  SPC_CHECK_ARG(proj ? (Cf == 0) : (feat || Cf == 0), "sa_fused: missing layer-0 operands");
   const long long rows = (long long)B * npoint * nsample;
   if (rows % SA_ROWS != 0 || ((long long)npoint * nsample) % SA_ROWS != 0) {
     set_error("sa_fused: npoint*nsample=%lld is not a multiple of %d", (long long)npoint * nsample, SA_ROWS);
@@ -842,24 +617,16 @@ extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, cons
     return SPC_ERR_UNSUPPORTED;
   }
   SaFusedParams p;
-  p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.G = G; p.Hc = Hc; p.feat = feat; p.W0 = W0;
-  p.b0 = b0; p.Cf = Cf; p.radius = radius;
+  p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.G = (const __nv_bfloat16 *)G_bf16; p.feat = feat;
+  p.W0 = W0; p.b0 = b0; p.Cf = Cf; p.radius = radius;
   p.W1 = (const __nv_bfloat16 *)W1_bf16; p.b1 = b1; p.W2 = (const __nv_bfloat16 *)W2_bf16; p.b2 = b2;
-  p.out = out; p.B = B; p.n = n; p.np = npoint; p.ns = nsample;
+  p.out = out; p.out_pm = (__nv_bfloat16 *)out_pm_bf16; p.B = B; p.n = n; p.np = npoint; p.ns = nsample;
   p.num_tiles = (int)(rows / SA_ROWS);
-  p.desc_swap = 0;
-  if (const char *e = getenv("SPC_SA_DESC_SWAP")) p.desc_swap = atoi(e);
   cudaStream_t stream = (cudaStream_t)stream_;
-  // SPC_SA_PIPE=0 selects the serial kernel (kept for A/B measurements)
-  const char *pe = getenv("SPC_SA_PIPE");
-  const bool pipe = !(pe && atoi(pe) == 0);
 #define SA_TRY(c1, c2, c3, ns)                                                                       \
-  if (C1 == c1 && C2 == c2 && C3 == c3 && nsample == ns) {                                           \
-    if (pipe)                                                                                        \
-      return proj ? launch_sa_pipe<c1, c2, c3, ns, true>(p, stream)                                  \
-                  : launch_sa_pipe<c1, c2, c3, ns, false>(p, stream);                                \
-    return proj ? launch_sa<c1, c2, c3, ns, true>(p, stream) : launch_sa<c1, c2, c3, ns, false>(p, stream); \
-  }
+  if (C1 == c1 && C2 == c2 && C3 == c3 && nsample == ns)                                             \
+    return proj ? launch_sa_pipe<c1, c2, c3, ns, true>(p, stream)                                    \
+                : launch_sa_pipe<c1, c2, c3, ns, false>(p, stream);
   SA_TRY(64, 64, 128, 64)      // SA1
   SA_TRY(64, 64, 128, 32)
   SA_TRY(64, 64, 128, 16)

@@ -77,6 +77,20 @@ class _FoldedMLP:
     def __init__(self):
         self.key = None
         self.data = None
+        self._w0f_t = None
+        self._w0x = None
+
+    def w0f_t(self, W0):
+        """(Cf, C1) bf16: feature columns of the folded conv0, transposed for the projection GEMM."""
+        if self._w0f_t is None:
+            self._w0f_t = W0[:, 3:].t().contiguous().to(torch.bfloat16)
+        return self._w0f_t
+
+    def w0x(self, W0):
+        """(C1, 3) f32: xyz columns of the folded conv0."""
+        if self._w0x is None:
+            self._w0x = W0[:, :3].contiguous()
+        return self._w0x
 
     def get(self, mlp):
         tensors = [t for t in list(mlp.parameters()) + list(mlp.buffers())]
@@ -84,6 +98,7 @@ class _FoldedMLP:
         if key != self.key:
             self.key = key
             self.data = None
+            self._w0f_t = self._w0x = None
             blocks = list(mlp.children())
             if len(blocks) == 3:
                 folded = [_fold_conv_bn(b) for b in blocks]
@@ -226,15 +241,20 @@ class PointnetSAModuleVotes(nn.Module):
         try:
             if Cf <= INLINE_MAX_FEATURES:
                 feat = None if features is None else features.contiguous()
-                return _ext.sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, feat=feat, W0=W0,
-                                             b0=b0, radius=radius)
-            # conv0 hoisted out of the grouping: per-point projection + per-centre bias
-            Wx = W0[:, :3] / radius
-            G = torch.matmul(features.transpose(1, 2), W0[:, 3:].t())
-            G += torch.matmul(xyz, Wx.t())
-            Hc = b0 - torch.matmul(new_xyz, Wx.t())
-            return _ext.sa_fused_forward(xyz, new_xyz, idx, W1, b1, W2, b2, G=G.contiguous(),
-                                         Hc=Hc.contiguous())
+                out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, feat=feat,
+                                                    radius=radius, want_point_major=True)
+            else:
+                # conv0 hoisted out of the grouping: ONE bf16 GEMM over the n points gives the
+                # per-point feature projection; the xyz columns stay in fp32 inside the kernel
+                pm = getattr(features, "_spc_pm", None)        # point-major bf16 copy from the producer
+                if pm is None or pm.shape != (features.shape[0], features.shape[2], Cf):
+                    pm = features.transpose(1, 2).to(torch.bfloat16)
+                Bn = pm.shape[0] * pm.shape[1]
+                G = torch.mm(pm.reshape(Bn, Cf), cache.w0f_t(W0)).view(pm.shape[0], pm.shape[1], -1)
+                out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, cache.w0x(W0), b0, W1, b1, W2, b2,
+                                                    G=G, radius=radius, want_point_major=True)
+            out._spc_pm = out_pm       # lets the next layer skip its transpose + cast
+            return out
         except _lib.SpcUnsupported:
             return None
 

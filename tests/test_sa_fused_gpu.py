@@ -86,14 +86,22 @@ def test_fused_matches_bf16_emulation(name):
         gx = U.grouping_operation(xyz.transpose(1, 2).contiguous(), idx)
         gx = (gx - new_xyz.transpose(1, 2).unsqueeze(-1)) / radius
         x = gx if feats is None else torch.cat([gx, U.grouping_operation(feats, idx)], 1)   # (B,K0,np,ns)
-        h1 = torch.relu(torch.einsum("ok,bkps->bops", W0, x) + b0[None, :, None, None])
+        if Cf > M.INLINE_MAX_FEATURES:
+            # projected form: the per-point feature projection is a bf16 GEMM output (bf16 inputs,
+            # fp32 accumulate, bf16 result); the xyz columns and the bias stay in fp32
+            fb = feats.to(torch.bfloat16).float()
+            G = torch.einsum("ok,bkn->bon", W0[:, 3:].to(torch.bfloat16).float(), fb).to(torch.bfloat16).float()
+            Gg = U.grouping_operation(G.contiguous(), idx)
+            h1 = torch.relu(Gg + torch.einsum("ok,bkps->bops", W0[:, :3], gx) + b0[None, :, None, None])
+        else:
+            h1 = torch.relu(torch.einsum("ok,bkps->bops", W0, x) + b0[None, :, None, None])
         h1 = h1.to(torch.bfloat16).float()
         h2 = torch.relu(torch.einsum("ok,bkps->bops", W1.float(), h1) + b1[None, :, None, None])
         h2 = h2.to(torch.bfloat16).float()
         h3 = torch.einsum("ok,bkps->bops", W2.float(), h2)
         want = torch.relu(h3.max(-1).values + b2[None, :, None])
     scale = want.abs().max().item()
-    assert (got - want).abs().max().item() <= 4e-3 * scale, name
+    assert (got - want).abs().max().item() <= 6e-3 * scale, name
 
 
 def test_fused_not_used_in_training_or_with_grad():
