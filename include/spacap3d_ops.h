@@ -138,6 +138,31 @@ int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *
                          const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample,
                          int C1, int C2, int C3, float *out, void *out_pm_bf16, void *stream);
 
+/* ---- point-major (BF16) eval path of the feature-propagation and voting stages ------------------
+ * These have no C++ counterpart in the reference; each replaces a chain of small ATen launches. */
+
+/* three_nn + inverse-distance weights (pointnet2_modules.py:398-402): idx (B,n,3) bit-identical to
+ * spc_three_nn; weight (B,n,3) = normalised 1/(dist+1e-8).  Needs m >= 3. */
+int spc_three_nn_weights(const float *unknown, const float *known, int B, int n, int m, int32_t *idx,
+                         float *weight, void *stream);
+
+/* three_interpolate + torch.cat with the skip features (pointnet2_modules.py:404-416), BF16
+ * point-major: known_pm (B,m,C2), skip_pm (B,n,C1) -> X (B,n,C2+C1).  C2, C1 multiples of 8. */
+int spc_interp_cat_pm(const void *known_pm_bf16, const int32_t *idx, const float *weight,
+                      const void *skip_pm_bf16, int B, int n, int m, int C2, int C1, void *X_bf16,
+                      void *stream);
+
+/* Voting tail (models/voting_module.py:52-61 + models/SpaCapNet.py:66-67), vote_factor 1:
+ * net (B*S,3+D) f32 = last voting conv WITHOUT bias, point-major; bias (3+D); seed_xyz (B,S,3);
+ * seed_pm (B,S,D) BF16 -> vote_xyz (B,S,3), L2-normalised vote features channel-major f32 (B,D,S)
+ * and point-major BF16 (B,S,D).  D <= 256. */
+int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz, const void *seed_pm_bf16,
+                  int B, int S, int D, float *vote_xyz, float *vote_feat_cm, void *vote_pm_bf16,
+                  void *stream);
+
+/* point-major BF16 (B,n,C) -> channel-major f32 (B,C,n) */
+int spc_pm_to_cm(const void *pm_bf16, int B, int n, int C, float *cm, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

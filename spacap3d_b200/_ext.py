@@ -237,3 +237,65 @@ def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=
                   b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), B, n, npoint, nsample, C1, C2, C3,
                   out.data_ptr(), out_pm.data_ptr() if out_pm is not None else None, _stream())
     return (out, out_pm) if want_point_major else out
+
+
+def three_nn_weights(unknown, known):
+    """three_nn + normalised inverse-distance weights in one kernel -> (idx (B,n,3) i32, weight (B,n,3) f32)
+    (pointnet2_modules.py:398-402)."""
+    _check(unknown, "unknown", torch.float32)
+    _check(known, "known", torch.float32)
+    _same_device(unknown, known)
+    B, n, _ = unknown.shape
+    m = known.shape[1]
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknown.device)
+    w = torch.empty((B, n, 3), dtype=torch.float32, device=unknown.device)
+    with torch.cuda.device(unknown.device):
+        _lib.call("spc_three_nn_weights", unknown.data_ptr(), known.data_ptr(), B, n, m, idx.data_ptr(),
+                  w.data_ptr(), _stream())
+    return idx, w
+
+
+def interp_cat_pm(known_pm, idx, weight, skip_pm):
+    """Point-major bf16: X (B,n,C2+C1) = [3-NN interpolation of known_pm (B,m,C2), skip_pm (B,n,C1)]."""
+    _check(known_pm, "known_pm", torch.bfloat16)
+    _check(idx, "idx", torch.int32)
+    _check(weight, "weight", torch.float32)
+    _check(skip_pm, "skip_pm", torch.bfloat16)
+    _same_device(known_pm, idx, weight, skip_pm)
+    B, m, C2 = known_pm.shape
+    n, C1 = skip_pm.shape[1], skip_pm.shape[2]
+    X = torch.empty((B, n, C2 + C1), dtype=torch.bfloat16, device=known_pm.device)
+    with torch.cuda.device(known_pm.device):
+        _lib.call("spc_interp_cat_pm", known_pm.data_ptr(), idx.data_ptr(), weight.data_ptr(), skip_pm.data_ptr(),
+                  B, n, m, C2, C1, X.data_ptr(), _stream())
+    return X
+
+
+def vote_tail(net, bias, seed_xyz, seed_pm):
+    """Voting tail: net (B*S,3+D) f32 (no bias), bias (3+D), seed_xyz (B,S,3), seed_pm (B,S,D) bf16 ->
+    vote_xyz (B,S,3), vote features L2-normalised: channel-major f32 (B,D,S) and point-major bf16 (B,S,D)."""
+    _check(net, "net", torch.float32)
+    _check(bias, "bias", torch.float32)
+    _check(seed_xyz, "seed_xyz", torch.float32)
+    _check(seed_pm, "seed_pm", torch.bfloat16)
+    _same_device(net, bias, seed_xyz, seed_pm)
+    B, S, D = seed_pm.shape
+    assert net.shape == (B * S, 3 + D) and bias.numel() == 3 + D
+    vote_xyz = torch.empty((B, S, 3), dtype=torch.float32, device=net.device)
+    cm = torch.empty((B, D, S), dtype=torch.float32, device=net.device)
+    pm = torch.empty((B, S, D), dtype=torch.bfloat16, device=net.device)
+    with torch.cuda.device(net.device):
+        _lib.call("spc_vote_tail", net.data_ptr(), bias.data_ptr(), seed_xyz.data_ptr(), seed_pm.data_ptr(), B, S, D,
+                  vote_xyz.data_ptr(), cm.data_ptr(), pm.data_ptr(), _stream())
+    return vote_xyz, cm, pm
+
+
+def pm_to_cm(pm):
+    """(B,n,C) bf16 point-major -> (B,C,n) f32 channel-major."""
+    _check(pm, "pm", torch.bfloat16)
+    _same_device(pm)
+    B, n, C = pm.shape
+    cm = torch.empty((B, C, n), dtype=torch.float32, device=pm.device)
+    with torch.cuda.device(pm.device):
+        _lib.call("spc_pm_to_cm", pm.data_ptr(), B, n, C, cm.data_ptr(), _stream())
+    return cm

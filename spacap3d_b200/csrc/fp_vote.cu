@@ -1,0 +1,240 @@
+// fp_vote.cu -- small fused kernels around the point-major (bf16) eval path of the detector's
+// feature-propagation and voting stages.  They replace chains of tiny
+// ATen launches (sqrt/add/reciprocal/sum/div, cat, transpose copies, norm/div; ~18 % of the SM time
+// of a forward, profiles/r1_sm_cycles_per_kernel_one_forward.csv) with one kernel each.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace spc {
+
+// ------------------------------------------------------------------------------------------------
+// three_nn + inverse-distance weights in one kernel.
+// PointnetFPModule.forward (reference pointnet2_modules.py:398-402):
+//   dist, idx = three_nn(unknown, known);  dist_recip = 1.0 / (dist + 1e-8)
+//   norm = sum(dist_recip, dim=2);          weight = dist_recip / norm
+// Same arithmetic (IEEE sqrt / div, left-to-right sum); idx is bit-identical to three_nn.
+// ------------------------------------------------------------------------------------------------
+constexpr int NW_THREADS = 128;
+constexpr int NW_TILE = 1024;
+
+__global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const float *__restrict__ unknown,
+                                                                       const float *__restrict__ known, int n,
+                                                                       int m, int32_t *__restrict__ idx,
+                                                                       float *__restrict__ weight) {
+  __shared__ float sx[NW_TILE], sy[NW_TILE], sz[NW_TILE];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * NW_THREADS + threadIdx.x;
+  const float *U = unknown + (size_t)b * n * 3;
+  const float *K = known + (size_t)b * m * 3;
+  const bool ok = j < n;
+  const float ux = ok ? __ldg(U + 3 * j + 0) : 0.f, uy = ok ? __ldg(U + 3 * j + 1) : 0.f,
+              uz = ok ? __ldg(U + 3 * j + 2) : 0.f;
+  float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int base = 0; base < m; base += NW_TILE) {
+    const int tile = min(NW_TILE, m - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tile * 3; e += NW_THREADS) {
+      const float v = __ldg(K + (size_t)base * 3 + e);
+      const int pt = e / 3, comp = e - pt * 3;
+      (comp == 0 ? sx : comp == 1 ? sy : sz)[pt] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < tile; ++k) {
+      const float d = sqdist_ref(ux, uy, uz, sx[k], sy[k], sz[k]);
+      if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = base + k; }
+      else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = base + k; }
+      else if (d < b3) { b3 = d; i3 = base + k; }
+    }
+  }
+  if (ok) {
+    const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
+    const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
+    const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
+    float *w = weight + ((size_t)b * n + j) * 3;
+    int32_t *oi = idx + ((size_t)b * n + j) * 3;
+    w[0] = __fdiv_rn(r1, norm); w[1] = __fdiv_rn(r2, norm); w[2] = __fdiv_rn(r3, norm);
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// three_interpolate + concat with the skip features, point-major bf16 in and out:
+//   X[b, j, 0:C2]      = sum_t w[b,j,t] * known_pm[b, idx[b,j,t], :]     (fp32 accumulate)
+//   X[b, j, C2:C2+C1]  = skip_pm[b, j, :]
+// (reference: three_interpolate + torch.cat, pointnet2_modules.py:404-416, there on (B,C,n) fp32).
+// One warp per point; lanes stride over 8-channel (16-byte) chunks => coalesced rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __nv_bfloat16 *__restrict__ known_pm,
+                                                            const int32_t *__restrict__ idx,
+                                                            const float *__restrict__ weight,
+                                                            const __nv_bfloat16 *__restrict__ skip_pm, int n,
+                                                            int m, int C2, int C1,
+                                                            __nv_bfloat16 *__restrict__ X) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int32_t *ix = idx + ((size_t)b * n + j) * 3;
+  const float *w = weight + ((size_t)b * n + j) * 3;
+  const int a1 = __ldg(ix), a2 = __ldg(ix + 1), a3 = __ldg(ix + 2);
+  const float w1 = __ldg(w), w2 = __ldg(w + 1), w3 = __ldg(w + 2);
+  const uint4 *r1 = reinterpret_cast<const uint4 *>(known_pm + ((size_t)b * m + a1) * C2);
+  const uint4 *r2 = reinterpret_cast<const uint4 *>(known_pm + ((size_t)b * m + a2) * C2);
+  const uint4 *r3 = reinterpret_cast<const uint4 *>(known_pm + ((size_t)b * m + a3) * C2);
+  uint4 *out = reinterpret_cast<uint4 *>(X + ((size_t)b * n + j) * (C2 + C1));
+  for (int c = lane; c < C2 / 8; c += 32) {
+    const uint4 v1 = __ldg(r1 + c), v2 = __ldg(r2 + c), v3 = __ldg(r3 + c);
+    const uint32_t p1[4] = {v1.x, v1.y, v1.z, v1.w}, p2[4] = {v2.x, v2.y, v2.z, v2.w}, p3[4] = {v3.x, v3.y, v3.z, v3.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      // same contraction order as three_interpolate: fma(p3,w3, fma(p1,w1, p2*w2))
+      const float lo = fmaf(__uint_as_float(p3[q] << 16), w3, fmaf(__uint_as_float(p1[q] << 16), w1, __uint_as_float(p2[q] << 16) * w2));
+      const float hi = fmaf(__uint_as_float(p3[q] & 0xffff0000u), w3,
+                            fmaf(__uint_as_float(p1[q] & 0xffff0000u), w1, __uint_as_float(p2[q] & 0xffff0000u) * w2));
+      __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      o[q] = *reinterpret_cast<uint32_t *>(&pk);
+    }
+    out[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  const uint4 *sk = reinterpret_cast<const uint4 *>(skip_pm + ((size_t)b * n + j) * C1);
+  for (int c = lane; c < C1 / 8; c += 32) out[C2 / 8 + c] = __ldg(sk + c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Voting tail (reference models/voting_module.py:52-61 + models/SpaCapNet.py:66-67), vote_factor 1:
+//   net (B*S, 3+D) fp32 = conv3 output WITHOUT bias (point-major), bias (3+D)
+//   vote_xyz[b,s,:]      = seed_xyz[b,s,:] + net[.,0:3] + bias[0:3]
+//   v                    = seed_feat[b,s,:] + net[.,3:] + bias[3:]
+//   vote_features[b,:,s] = v / ||v||_2          (channel-major fp32, the tensor the reference exposes)
+//   vote_pm[b,s,:]       = same, point-major bf16 (input of the vote-aggregation projection GEMM)
+// One CTA per 32 seeds: a warp normalises one seed at a time (lanes over channels), the tile is
+// transposed through shared memory so that the channel-major store is coalesced along seeds.
+// ------------------------------------------------------------------------------------------------
+constexpr int VT_SEEDS = 32;
+
+__global__ void __launch_bounds__(256) vote_tail_kernel(const float *__restrict__ net, const float *__restrict__ bias,
+                                                        const float *__restrict__ seed_xyz,
+                                                        const __nv_bfloat16 *__restrict__ seed_pm, int S, int D,
+                                                        float *__restrict__ vote_xyz,
+                                                        float *__restrict__ vote_feat_cm,
+                                                        __nv_bfloat16 *__restrict__ vote_pm) {
+  extern __shared__ float s_tile[];                  // [D][VT_SEEDS + 1]
+  const int b = blockIdx.y;
+  const int s0 = blockIdx.x * VT_SEEDS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = 3 + D;
+  for (int t = warp; t < VT_SEEDS; t += 8) {
+    const int s = s0 + t;
+    if (s >= S) break;                               // warp-uniform
+    const float *row = net + ((size_t)b * S + s) * ld;
+    if (lane < 3)
+      vote_xyz[((size_t)b * S + s) * 3 + lane] = __ldg(seed_xyz + ((size_t)b * S + s) * 3 + lane) + __ldg(row + lane) + __ldg(bias + lane);
+    const __nv_bfloat16 *sf = seed_pm + ((size_t)b * S + s) * D;
+    float v[8];                                      // D <= 256: channel c = lane + 32*i
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < D ? __bfloat162float(sf[c]) + __ldg(row + 3 + c) + __ldg(bias + 3 + c) : 0.f;
+      ss = fmaf(v[i], v[i], ss);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.0f / sqrtf(ss);
+    __nv_bfloat16 *op = vote_pm + ((size_t)b * S + s) * D;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < D) {
+        const float r = v[i] * inv;
+        s_tile[c * (VT_SEEDS + 1) + t] = r;
+        op[c] = __float2bfloat16_rn(r);
+      }
+    }
+  }
+  __syncthreads();
+  const int nseed = min(VT_SEEDS, S - s0);
+  for (int e = threadIdx.x; e < D * VT_SEEDS; e += 256) {
+    const int c = e / VT_SEEDS, t = e - c * VT_SEEDS;
+    if (t < nseed) vote_feat_cm[((size_t)b * D + c) * S + s0 + t] = s_tile[c * (VT_SEEDS + 1) + t];
+  }
+}
+
+// point-major bf16 (B,n,C) -> channel-major fp32 (B,C,n)   (tile transpose through shared memory)
+__global__ void __launch_bounds__(256) pm_to_cm_kernel(const __nv_bfloat16 *__restrict__ pm, int n, int C,
+                                                       float *__restrict__ cm) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    t[r][tx] = (p < n && c < C) ? __bfloat162float(pm[((size_t)b * n + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < n) cm[((size_t)b * C + c) * n + p] = t[tx][r];
+  }
+}
+
+}  // namespace spc
+
+using namespace spc;
+
+extern "C" int spc_three_nn_weights(const float *unknown, const float *known, int B, int n, int m,
+                                    int32_t *idx, float *weight, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && n >= 0 && m >= 3, "three_nn_weights: need m >= 3 known points");
+  if (B == 0 || n == 0) return SPC_OK;
+  SPC_CHECK_ARG(unknown && known && idx && weight, "three_nn_weights: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "three_nn_weights: B too large");
+  three_nn_weights_kernel<<<dim3(ceil_div(n, NW_THREADS), B), NW_THREADS, 0, (cudaStream_t)stream_>>>(
+      unknown, known, n, m, idx, weight);
+  SPC_LAUNCH_CHECK("three_nn_weights_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_interp_cat_pm(const void *known_pm_bf16, const int32_t *idx, const float *weight,
+                                 const void *skip_pm_bf16, int B, int n, int m, int C2, int C1,
+                                 void *X_bf16, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && n >= 0 && m >= 1 && C2 >= 8 && C1 >= 0, "interp_cat_pm: bad sizes");
+  SPC_CHECK_ARG(C2 % 8 == 0 && C1 % 8 == 0, "interp_cat_pm: channel counts must be multiples of 8");
+  if (B == 0 || n == 0) return SPC_OK;
+  SPC_CHECK_ARG(known_pm_bf16 && idx && weight && X_bf16 && (skip_pm_bf16 || C1 == 0), "interp_cat_pm: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "interp_cat_pm: B too large");
+  interp_cat_pm_kernel<<<dim3(ceil_div(n, 8), B), 256, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16 *)known_pm_bf16, idx, weight, (const __nv_bfloat16 *)skip_pm_bf16, n, m, C2, C1,
+      (__nv_bfloat16 *)X_bf16);
+  SPC_LAUNCH_CHECK("interp_cat_pm_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz,
+                             const void *seed_pm_bf16, int B, int S, int D, float *vote_xyz,
+                             float *vote_feat_cm, void *vote_pm_bf16, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && S >= 0 && D >= 1 && D <= 256, "vote_tail: feature dim must be in 1..256");
+  if (B == 0 || S == 0) return SPC_OK;
+  SPC_CHECK_ARG(net && bias && seed_xyz && seed_pm_bf16 && vote_xyz && vote_feat_cm && vote_pm_bf16, "vote_tail: null pointer");
+  SPC_CHECK_ARG(B <= 65535, "vote_tail: B too large");
+  const size_t smem = (size_t)D * (VT_SEEDS + 1) * sizeof(float);
+  vote_tail_kernel<<<dim3(ceil_div(S, VT_SEEDS), B), 256, smem, (cudaStream_t)stream_>>>(
+      net, bias, seed_xyz, (const __nv_bfloat16 *)seed_pm_bf16, S, D, vote_xyz, vote_feat_cm,
+      (__nv_bfloat16 *)vote_pm_bf16);
+  SPC_LAUNCH_CHECK("vote_tail_kernel");
+  return SPC_OK;
+}
+
+extern "C" int spc_pm_to_cm(const void *pm_bf16, int B, int n, int C, float *cm, void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && n >= 0 && C >= 0, "pm_to_cm: bad sizes");
+  if (B == 0 || n == 0 || C == 0) return SPC_OK;
+  SPC_CHECK_ARG(pm_bf16 && cm, "pm_to_cm: null pointer");
+  SPC_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "pm_to_cm: B or C too large");
+  pm_to_cm_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32), B), 256, 0, (cudaStream_t)stream_>>>(
+      (const __nv_bfloat16 *)pm_bf16, n, C, cm);
+  SPC_LAUNCH_CHECK("pm_to_cm_kernel");
+  return SPC_OK;
+}

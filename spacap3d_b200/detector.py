@@ -18,7 +18,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .pointnet2_modules import PointnetFPModule, PointnetSAModuleVotes
+from . import _ext
+from .pointnet2_modules import FoldedChain, PointnetFPModule, PointnetSAModuleVotes, fast_eval_ok
 
 # ScanNet per-class mean box sizes (18 x 3, float64): dataset metadata shipped by the reference as
 # data/scannet/meta_data/scannet_reference_means.npz, read by ScannetDatasetConfig
@@ -112,6 +113,25 @@ class VotingModule(nn.Module):
         vote_features = vote_features.contiguous().view(B, S * self.vote_factor, self.out_dim)
         return vote_xyz, vote_features.transpose(2, 1).contiguous()
 
+    def forward_normalized_fast(self, seed_xyz, seed_features):
+        """Eval fast path returning (vote_xyz, L2-normalised vote_features) or None: three point-major
+        bf16 GEMMs (BN folded, bias+ReLU in the GEMM epilogue, the last one with fp32 output) and ONE
+        tail kernel for offsets, residual, normalisation and both output layouts."""
+        pm = getattr(seed_features, "_spc_pm", None)
+        if (self.training or self.vote_factor != 1 or pm is None or self.out_dim > 256
+                or not fast_eval_ok(seed_xyz, seed_features)):
+            return None
+        chain = self.__dict__.setdefault("_chain", FoldedChain()).get(
+            [(self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, None)])
+        B, S, D = pm.shape
+        h = pm.reshape(B * S, D)
+        h = torch._addmm_activation(chain[0][1], h, chain[0][0])
+        h = torch._addmm_activation(chain[1][1], h, chain[1][0])
+        net = torch.mm(h, chain[2][0], out_dtype=torch.float32)          # (B*S, 3+D), bias added in the tail
+        vote_xyz, vote_features, vote_pm = _ext.vote_tail(net, chain[2][2], seed_xyz.contiguous(), pm)
+        vote_features._spc_pm = vote_pm
+        return vote_xyz, vote_features
+
 
 class ProposalModule(nn.Module):
     def __init__(self, num_class, num_heading_bin, num_size_cluster, mean_size_arr, num_proposal,
@@ -146,6 +166,15 @@ class ProposalModule(nn.Module):
         data_dict["aggregated_vote_xyz"] = xyz
         data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
         data_dict["aggregated_vote_inds"] = fps_inds
+        pm = getattr(features, "_spc_pm", None)
+        if not self.training and pm is not None and fast_eval_ok(features):
+            chain = self.__dict__.setdefault("_chain", FoldedChain()).get(
+                [(self.proposal[0], self.proposal[1]), (self.proposal[3], self.proposal[4]), (self.proposal[6], None)])
+            B, K, D = pm.shape
+            h = torch._addmm_activation(chain[0][1], pm.reshape(B * K, D), chain[0][0])
+            h = torch._addmm_activation(chain[1][1], h, chain[1][0])
+            t = torch.addmm(chain[2][2], h.float(), chain[2][0].float()).view(B, K, -1)   # fp32 head output
+            return self.decode_scores(None, data_dict, net_transposed=t)
         net = self.proposal(features)
         return self.decode_scores(net, data_dict)
 
@@ -160,9 +189,9 @@ class ProposalModule(nn.Module):
         corners = self._corner_signs * (box_size / 2).unsqueeze(-2)                   # (B,K,8,3)
         return corners + center.unsqueeze(-2)
 
-    def decode_scores(self, net, data_dict):
+    def decode_scores(self, net, data_dict, net_transposed=None):
         nh, ns = self.num_heading_bin, self.num_size_cluster
-        t = net.transpose(2, 1).contiguous()                                          # (B,K,out)
+        t = net.transpose(2, 1).contiguous() if net_transposed is None else net_transposed   # (B,K,out)
         B, K = t.shape[0], t.shape[1]
         objectness_scores = t[:, :, 0:2]
         center = data_dict["aggregated_vote_xyz"] + t[:, :, 2:5]
@@ -213,8 +242,12 @@ class VoteNetDetector(nn.Module):
         data_dict["seed_inds"] = data_dict["fp2_inds"]
         data_dict["seed_xyz"] = xyz
         data_dict["seed_features"] = features
-        xyz, features = self.vgen(xyz, features)
-        features = features.div(torch.norm(features, p=2, dim=1).unsqueeze(1))
+        fast = self.vgen.forward_normalized_fast(xyz, features)
+        if fast is not None:
+            xyz, features = fast
+        else:
+            xyz, features = self.vgen(xyz, features)
+            features = features.div(torch.norm(features, p=2, dim=1).unsqueeze(1))
         data_dict["vote_xyz"] = xyz
         data_dict["vote_features"] = features
         return self.proposal(xyz, features, data_dict)

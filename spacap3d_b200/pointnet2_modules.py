@@ -110,6 +110,46 @@ class _FoldedMLP:
         return self.data
 
 
+def fold_conv_bn_pair(conv, bn):
+    """(W (Cout,Cin) f32, b (Cout) f32) of a 1x1 conv followed by an optional eval-mode BatchNorm."""
+    W = conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(conv.out_channels, device=W.device)
+    if bn is not None:
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        W = W * scale[:, None]
+        b = (b - bn.running_mean) * scale + bn.bias.detach()
+    return W, b
+
+
+class FoldedChain:
+    """Cache of a conv(+BN)(+ReLU) chain as point-major GEMM operands: [(W^T (Cin,Cout) bf16, b bf16)],
+    refreshed when a parameter / running statistic changes (tensor versions)."""
+
+    def __init__(self):
+        self.key = None
+        self.layers = None
+
+    def get(self, pairs):
+        """pairs: list of (conv, bn_or_None)."""
+        tensors = []
+        for conv, bn in pairs:
+            tensors += list(conv.parameters()) + (list(bn.parameters()) + list(bn.buffers()) if bn is not None else [])
+        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        if key != self.key:
+            self.key = key
+            self.layers = []
+            for conv, bn in pairs:
+                W, b = fold_conv_bn_pair(conv, bn)
+                self.layers.append((W.t().contiguous().to(torch.bfloat16), b.to(torch.bfloat16).contiguous(),
+                                    b.contiguous()))
+        return self.layers
+
+
+def fast_eval_ok(*tensors):
+    """The bf16 point-major fast paths apply in eval-style use only: no autograd, CUDA tensors."""
+    return FAST_PATHS and not torch.is_grad_enabled() and all(t is not None and t.is_cuda for t in tensors)
+
+
 def _pool_max(x):
     """(B,C,npoint,nsample) -> (B,C,npoint)"""
     return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
@@ -289,6 +329,9 @@ class PointnetFPModule(nn.Module):
                 known_feats: torch.Tensor) -> torch.Tensor:
         """unknown (B,n,3), known (B,m,3), unknow_feats (B,C1,n), known_feats (B,C2,m)
         -> (B,mlp[-1],n)"""
+        fast = self._forward_fast(unknown, known, unknow_feats, known_feats)
+        if fast is not None:
+            return fast
         if known is not None:
             dist, idx = pointnet2_utils.three_nn(unknown, known)
             dist_recip = 1.0 / (dist + 1e-8)
@@ -300,6 +343,37 @@ class PointnetFPModule(nn.Module):
         new_features = interpolated_feats if unknow_feats is None else \
             torch.cat([interpolated_feats, unknow_feats], dim=1)
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
+
+
+    # -- bf16 point-major eval path -------------------------------------------------------------------
+    def _forward_fast(self, unknown, known, unknow_feats, known_feats):
+        """three_nn+weights (1 kernel) -> interpolate+concat (1 kernel, point-major bf16) -> one
+        cuBLASLt GEMM with fused bias+ReLU per MLP layer -> channel-major fp32 copy for the API.
+        Needs the point-major bf16 copies that the fused SA / FP kernels attach to their outputs."""
+        if self.training or known is None or not fast_eval_ok(unknown, known, unknow_feats, known_feats):
+            return None
+        kpm, spm = getattr(known_feats, "_spc_pm", None), getattr(unknow_feats, "_spc_pm", None)
+        if kpm is None or spm is None or known.shape[1] < 3 or kpm.shape[2] % 8 or spm.shape[2] % 8:
+            return None
+        pairs = []
+        for block in self.mlp.children():
+            conv, norm, act = getattr(block, "conv", None), getattr(block, "bn", None), getattr(block, "activation", None)
+            if conv is None or not isinstance(act, nn.ReLU) or conv.kernel_size != (1, 1):
+                return None
+            pairs.append((conv, norm.bn if norm is not None else None))
+        chain = self.__dict__.setdefault("_chain", FoldedChain()).get(pairs)
+        if chain[0][0].shape[0] != kpm.shape[2] + spm.shape[2]:
+            return None
+        idx, weight = _ext.three_nn_weights(unknown.contiguous(), known.contiguous())
+        X = _ext.interp_cat_pm(kpm, idx, weight, spm)
+        B, n = X.shape[0], X.shape[1]
+        h = X.view(B * n, -1)
+        for Wt, b16, _ in chain:
+            h = torch._addmm_activation(b16, h, Wt)          # relu(h @ Wt + b), bias+ReLU in the GEMM epilogue
+        out_pm = h.view(B, n, -1)
+        out = _ext.pm_to_cm(out_pm)
+        out._spc_pm = out_pm
+        return out
 
 
 class PointnetLFPModuleMSG(nn.Module):

@@ -1,0 +1,129 @@
+"""Eval fast paths of the callers (FP modules, voting, proposal head, whole detector) against the
+reference op sequence in fp32 (FAST_PATHS off, TF32 off).  The fast paths run the 1x1-conv chains
+as bf16 GEMMs (fp32 accumulate) => tolerance 1e-2 .. 3e-2 of the tensor's max magnitude (north_star:
+"1e-2 for bf16 MLP"; errors compound over the nine bf16 stages of the full detector)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class fp32_reference:
+    def __enter__(self):
+        from spacap3d_b200 import pointnet2_modules as M
+        self.M = M
+        self.old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, M.FAST_PATHS)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        M.FAST_PATHS = False
+
+    def __exit__(self, *a):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, self.M.FAST_PATHS = self.old
+
+
+def _randomize_bn(model, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for mod in model.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+            mod.running_var.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+            mod.weight.data.copy_(torch.rand(mod.num_features, generator=g) * 0.5 + 0.75)
+            mod.bias.data.copy_(torch.randn(mod.num_features, generator=g) * 0.05)
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def test_three_nn_weights_matches_module_formula():
+    from spacap3d_b200 import _ext
+    g = torch.Generator(device="cpu").manual_seed(0)
+    unknown = (torch.rand(3, 700, 3, generator=g) * 4 - 2).to(DEV)
+    known = (torch.rand(3, 300, 3, generator=g) * 4 - 2).to(DEV)
+    known[0, :50] = unknown[0, :50]                                 # exact zero distances
+    idx, w = _ext.three_nn_weights(unknown, known)
+    d2, ridx = _ext.three_nn(unknown, known)
+    assert torch.equal(idx, ridx)
+    dist = torch.sqrt(d2)
+    recip = 1.0 / (dist + 1e-8)
+    want = recip / recip.sum(dim=2, keepdim=True)
+    torch.testing.assert_close(w, want, rtol=1e-6, atol=1e-7)
+
+
+def test_fp_module_fast_path():
+    from spacap3d_b200.pointnet2_modules import PointnetFPModule
+    torch.manual_seed(1)
+    fp = PointnetFPModule(mlp=[256 + 256, 256, 256]).to(DEV).eval()
+    _randomize_bn(fp, 2)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    unknown = (torch.rand(2, 512, 3, generator=g) * 6 - 3).to(DEV)
+    known = unknown[:, ::2].contiguous()
+    uf = torch.relu(torch.randn(2, 256, 512, generator=g)).to(DEV)
+    kf = torch.relu(torch.randn(2, 256, 256, generator=g)).to(DEV)
+    uf._spc_pm = uf.transpose(1, 2).contiguous().to(torch.bfloat16)
+    kf._spc_pm = kf.transpose(1, 2).contiguous().to(torch.bfloat16)
+    with torch.no_grad():
+        fast = fp(unknown, known, uf, kf)
+        assert getattr(fast, "_spc_pm", None) is not None           # the fast path ran
+        with fp32_reference():
+            ref = fp(unknown, known, uf, kf)
+    assert fast.shape == ref.shape == (2, 256, 512)
+    assert _rel(fast, ref) <= 1e-2
+    assert _rel(fast._spc_pm.float().transpose(1, 2), ref) <= 1e-2
+
+
+def test_voting_and_proposal_fast_paths():
+    from spacap3d_b200.detector import ProposalModule, VotingModule, SCANNET_MEAN_SIZE_ARR
+    torch.manual_seed(4)
+    vgen = VotingModule(1, 256).to(DEV).eval()
+    prop = ProposalModule(18, 1, 18, SCANNET_MEAN_SIZE_ARR, 256).to(DEV).eval()
+    _randomize_bn(vgen, 5)
+    _randomize_bn(prop, 6)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    seed_xyz = (torch.rand(2, 1024, 3, generator=g) * 6 - 3).to(DEV)
+    sf = torch.relu(torch.randn(2, 256, 1024, generator=g)).to(DEV)
+    sf._spc_pm = sf.transpose(1, 2).contiguous().to(torch.bfloat16)
+    with torch.no_grad():
+        fast = vgen.forward_normalized_fast(seed_xyz, sf)
+        assert fast is not None
+        vx, vf = fast
+        rx, rf = vgen(seed_xyz, sf)
+        rf = rf.div(torch.norm(rf, p=2, dim=1).unsqueeze(1))
+        assert (vx - rx).abs().max().item() <= 1e-2 * (rx - seed_xyz).abs().max().item() + 1e-5   # offsets
+        assert _rel(vf, rf) <= 1e-2
+        assert _rel(vf._spc_pm.float().transpose(1, 2), rf) <= 1e-2
+        # proposal module on identical inputs: FPS indices must agree bit for bit, scores to 2e-2
+        d_fast = prop(vx, vf, {})
+        with fp32_reference():
+            vf_plain = vf.clone()
+            d_ref = prop(vx, vf_plain, {})
+    assert torch.equal(d_fast["aggregated_vote_inds"], d_ref["aggregated_vote_inds"])
+    for k in ("objectness_scores", "center", "size_scores", "sem_cls_scores", "size_residuals"):
+        assert d_fast[k].shape == d_ref[k].shape
+        assert _rel(d_fast[k], d_ref[k]) <= 2e-2, k
+    assert d_fast["bbox_corner"].dtype == torch.float64 and d_fast["bbox_corner"].shape == (2, 256, 8, 3)
+
+
+def test_detector_backbone_and_votes_fast_vs_fp32():
+    """Whole backbone + voting: indices of SA1-4 bit-exact (they do not depend on features), seed and
+    vote features within 3e-2 of max after eight bf16 stages."""
+    from spacap3d_b200.detector import VoteNetDetector
+    from spacap3d_b200.scenes import make_scene
+    torch.manual_seed(0)
+    model = VoteNetDetector(input_feature_dim=1).to(DEV).eval()
+    _randomize_bn(model, 11)
+    pc = torch.from_numpy(np.stack([make_scene(31, 20000), make_scene(32, 20000, with_replacement=True)], 0)).to(DEV)
+    with torch.no_grad():
+        fast = model({"point_clouds": pc})
+        with fp32_reference():
+            ref = model({"point_clouds": pc})
+    for k in ("sa1_inds", "sa2_inds", "sa1_xyz", "sa4_xyz", "seed_inds"):
+        assert torch.equal(fast[k], ref[k]), k
+    for k, tol in (("sa1_features", 1e-2), ("sa4_features", 2e-2), ("fp2_features", 3e-2), ("vote_features", 3e-2)):
+        assert _rel(fast[k], ref[k]) <= tol, (k, _rel(fast[k], ref[k]))
+    off_f, off_r = fast["vote_xyz"] - fast["seed_xyz"], ref["vote_xyz"] - ref["seed_xyz"]
+    assert (off_f - off_r).abs().max().item() <= 3e-2 * off_r.abs().max().item()
+    for k in ("objectness_scores", "center", "bbox_corner", "sem_cls_scores", "aggregated_vote_inds"):
+        assert fast[k].shape == ref[k].shape and torch.isfinite(fast[k].double()).all()
