@@ -110,7 +110,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     N = xyz.shape[1]
     out = torch.empty((B, M, int(nsample)), dtype=torch.int32, device=new_xyz.device)
     with torch.cuda.device(new_xyz.device):
-        if N >= 4096:      # large clouds: uniform-grid search (bit-identical output)
+        if N >= 1024:      # uniform-grid search (bit-identical output); tiny clouds stay all-pairs
             nbytes = _lib.load().spc_ball_query_workspace_bytes(B, N)
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=new_xyz.device)
             _lib.call("spc_ball_query_ex", new_xyz.data_ptr(), xyz.data_ptr(), B, N, M, float(radius),

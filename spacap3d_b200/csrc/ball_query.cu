@@ -344,7 +344,7 @@ extern "C" int spc_ball_query_ex(const float *new_xyz, const float *xyz, int B, 
   SPC_CHECK_ARG(new_xyz && idx && (xyz || N == 0), "ball_query: null pointer");
   // the grid pays off once the all-pairs scan dominates; tiny clouds stay on the brute-force kernel
   const bool use_grid = workspace && workspace_bytes >= spc_ball_query_workspace_bytes(B, N) &&
-                        N >= 4096 && (long long)N * M >= (1LL << 22) && nsample <= 1024 && B <= 65535 &&
+                        N >= 1024 && (long long)N * M >= (1LL << 19) && nsample <= 1024 && B <= 65535 &&
                         radius > 0.f && !getenv("SPC_BQ_BRUTE");
   if (!use_grid) return ball_query_brute(new_xyz, xyz, B, N, M, radius, nsample, idx, stream_);
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -16,7 +16,17 @@ namespace spc {
 // Same arithmetic (IEEE sqrt / div, left-to-right sum); idx is bit-identical to three_nn.
 // ------------------------------------------------------------------------------------------------
 constexpr int NW_THREADS = 128;
+constexpr int NW_SPLIT = 4;          // lanes cooperating on one unknown point
 constexpr int NW_TILE = 1024;
+
+// insert candidate (d,i) into the ascending triple, ordering by (distance, index): the reference's
+// strict '<' scan in ascending k keeps the lower index on ties, which is exactly this order
+__device__ __forceinline__ void nn3_insert(float d, int i, float &b1, int &i1, float &b2, int &i2, float &b3,
+                                           int &i3) {
+  if (d < b1 || (d == b1 && i < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = i; }
+  else if (d < b2 || (d == b2 && i < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = i; }
+  else if (d < b3 || (d == b3 && i < i3)) { b3 = d; i3 = i; }
+}
 
 __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const float *__restrict__ unknown,
                                                                        const float *__restrict__ known, int n,
@@ -24,14 +34,15 @@ __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const floa
                                                                        float *__restrict__ weight) {
   __shared__ float sx[NW_TILE], sy[NW_TILE], sz[NW_TILE];
   const int b = blockIdx.y;
-  const int j = blockIdx.x * NW_THREADS + threadIdx.x;
+  const int sub = threadIdx.x & (NW_SPLIT - 1);
+  const int j = blockIdx.x * (NW_THREADS / NW_SPLIT) + (threadIdx.x >> 2);
   const float *U = unknown + (size_t)b * n * 3;
   const float *K = known + (size_t)b * m * 3;
   const bool ok = j < n;
   const float ux = ok ? __ldg(U + 3 * j + 0) : 0.f, uy = ok ? __ldg(U + 3 * j + 1) : 0.f,
               uz = ok ? __ldg(U + 3 * j + 2) : 0.f;
   float b1 = INFINITY, b2 = INFINITY, b3 = INFINITY;
-  int i1 = 0, i2 = 0, i3 = 0;
+  int i1 = 0x7fffffff, i2 = 0x7fffffff, i3 = 0x7fffffff;
   for (int base = 0; base < m; base += NW_TILE) {
     const int tile = min(NW_TILE, m - base);
     __syncthreads();
@@ -41,14 +52,25 @@ __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const floa
       (comp == 0 ? sx : comp == 1 ? sy : sz)[pt] = v;
     }
     __syncthreads();
-    for (int k = 0; k < tile; ++k) {
+    for (int k = sub; k < tile; k += NW_SPLIT) {       // each lane of the quad scans every 4th point
       const float d = sqdist_ref(ux, uy, uz, sx[k], sy[k], sz[k]);
       if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = base + k; }
       else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = base + k; }
       else if (d < b3) { b3 = d; i3 = base + k; }
     }
   }
-  if (ok) {
+  // merge the four partial triples (butterfly over the quad), ordered by (distance, index)
+#pragma unroll
+  for (int o = 1; o < NW_SPLIT; o <<= 1) {
+    const float c1 = __shfl_xor_sync(0xffffffffu, b1, o), c2 = __shfl_xor_sync(0xffffffffu, b2, o),
+                c3 = __shfl_xor_sync(0xffffffffu, b3, o);
+    const int k1 = __shfl_xor_sync(0xffffffffu, i1, o), k2 = __shfl_xor_sync(0xffffffffu, i2, o),
+              k3 = __shfl_xor_sync(0xffffffffu, i3, o);
+    nn3_insert(c1, k1, b1, i1, b2, i2, b3, i3);
+    nn3_insert(c2, k2, b1, i1, b2, i2, b3, i3);
+    nn3_insert(c3, k3, b1, i1, b2, i2, b3, i3);
+  }
+  if (ok && sub == 0) {
     const float r1 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b1), 1e-8f));
     const float r2 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b2), 1e-8f));
     const float r3 = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(b3), 1e-8f));
@@ -192,7 +214,7 @@ extern "C" int spc_three_nn_weights(const float *unknown, const float *known, in
   if (B == 0 || n == 0) return SPC_OK;
   SPC_CHECK_ARG(unknown && known && idx && weight, "three_nn_weights: null pointer");
   SPC_CHECK_ARG(B <= 65535, "three_nn_weights: B too large");
-  three_nn_weights_kernel<<<dim3(ceil_div(n, NW_THREADS), B), NW_THREADS, 0, (cudaStream_t)stream_>>>(
+  three_nn_weights_kernel<<<dim3(ceil_div(n, NW_THREADS / NW_SPLIT), B), NW_THREADS, 0, (cudaStream_t)stream_>>>(
       unknown, known, n, m, idx, weight);
   SPC_LAUNCH_CHECK("three_nn_weights_kernel");
   return SPC_OK;

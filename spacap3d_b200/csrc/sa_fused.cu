@@ -197,11 +197,13 @@ constexpr int SA_ROWS = 128;        // rows (centre,neighbour pairs) per tile
 constexpr int SA_MAX_K0 = 3 + 16;   // MODE_INLINE supports up to 16 raw feature channels
 constexpr int SA_W0_STRIDE = 20;    // floats per channel row of the inline layer-0 weights (K0+1 padded)
 
-// in-line layer 0 with KQ float4 groups of inputs: in = [(p-c)/r (3), features (Cf), 1 (bias), 0...]
-template <int C1, int NKC, int KQ>
+// In-line layer 0 with exactly NIN inputs: in = [(p-c)/r (3), features (Cf), 1 (bias)], NIN = 4+Cf.
+// Weights sit in shared memory transposed per 8-channel chunk, sW0t[kc][k][8], so that one input
+// updates 8 accumulators from two broadcast 16-byte reads and no FMA is spent on padding.
+template <int C1, int NKC, int NIN>
 __device__ __forceinline__ void sa_produce_inline(const SaFusedParams &p, int b, int j, int i, int r, int kc0,
-                                                  uint8_t *sH1, const float *sW0, int K0) {
-  float in[4 * KQ];
+                                                  uint8_t *sH1, const float *sW0t) {
+  float in[NIN];
   const float *pp = p.xyz + ((size_t)b * p.n + i) * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
   // (p - c) / r, exactly as grouped_xyz -= new_xyz; grouped_xyz /= radius
@@ -210,24 +212,21 @@ __device__ __forceinline__ void sa_produce_inline(const SaFusedParams &p, int b,
   in[2] = __fdiv_rn(__ldg(pp + 2) - __ldg(cc + 2), p.radius);
   const float *fp = p.feat + (size_t)b * p.Cf * p.n + i;
 #pragma unroll
-  for (int f = 3; f < 4 * KQ; ++f)
-    in[f] = f < K0 ? __ldg(fp + (size_t)(f - 3) * p.n) : (f == K0 ? 1.f : 0.f);
+  for (int f = 3; f < NIN - 1; ++f) in[f] = __ldg(fp + (size_t)(f - 3) * p.n);
+  in[NIN - 1] = 1.f;                                  // the folded bias rides along as the last "input"
 #pragma unroll 2
   for (int kc = kc0; kc < kc0 + NKC; ++kc) {
+    const float4 *w = reinterpret_cast<const float4 *>(sW0t + (size_t)kc * SA_W0_STRIDE * 8);
     float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 *w = reinterpret_cast<const float4 *>(sW0 + (size_t)(kc * 8 + c) * SA_W0_STRIDE);
-      float a = 0.f;
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
-      for (int g4 = 0; g4 < KQ; ++g4) {
-        const float4 wv = w[g4];
-        a = fmaf(wv.x, in[4 * g4 + 0], a);
-        a = fmaf(wv.y, in[4 * g4 + 1], a);
-        a = fmaf(wv.z, in[4 * g4 + 2], a);
-        a = fmaf(wv.w, in[4 * g4 + 3], a);
-      }
-      acc[c] = a;
+    for (int k = 0; k < NIN; ++k) {
+      const float4 wa = w[2 * k], wb = w[2 * k + 1];
+      acc[0] = fmaf(wa.x, in[k], acc[0]); acc[1] = fmaf(wa.y, in[k], acc[1]);
+      acc[2] = fmaf(wa.z, in[k], acc[2]); acc[3] = fmaf(wa.w, in[k], acc[3]);
+      acc[4] = fmaf(wb.x, in[k], acc[4]); acc[5] = fmaf(wb.y, in[k], acc[5]);
+      acc[6] = fmaf(wb.z, in[k], acc[6]); acc[7] = fmaf(wb.w, in[k], acc[7]);
     }
     uint4 o;
     o.x = pack_relu_bf16x2(acc[0], acc[1]);
@@ -381,8 +380,10 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
   }
   for (int e = tid; e < C2; e += SAP_THREADS) sB1[e] = __ldg(p.b1 + e);
   if (!MODE_PROJ) {
+    // sW0t[kc][k][c8]: weight of input k for channel kc*8+c8; k == K0 holds the folded bias
     for (int e = tid; e < C1 * SA_W0_STRIDE; e += SAP_THREADS) {
-      const int c = e / SA_W0_STRIDE, k = e - c * SA_W0_STRIDE;
+      const int kc = e / (SA_W0_STRIDE * 8), rem = e - kc * (SA_W0_STRIDE * 8);
+      const int k = rem >> 3, c = kc * 8 + (rem & 7);
       sW0[e] = k < K0 ? __ldg(p.W0 + (size_t)c * K0 + k) : (k == K0 ? __ldg(p.b0 + c) : 0.f);
     }
   }
@@ -438,12 +439,25 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         const int j = (int)(R - (long long)b * rows_per_scene) / p.ns;
         mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
         uint8_t *h1 = sH1 + s * L::H1_BYTES;
-        switch ((K0 + 1 + 3) >> 2) {
-          case 1: sa_produce_inline<C1, NKC, 1>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 2: sa_produce_inline<C1, NKC, 2>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 3: sa_produce_inline<C1, NKC, 3>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          case 4: sa_produce_inline<C1, NKC, 4>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
-          default: sa_produce_inline<C1, NKC, 5>(p, b, j, i, r, half * NKC, h1, sW0, K0); break;
+        switch (K0 + 1) {                                          // exact input count (warp-uniform)
+          case 4: sa_produce_inline<C1, NKC, 4>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 5: sa_produce_inline<C1, NKC, 5>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 6: sa_produce_inline<C1, NKC, 6>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 7: sa_produce_inline<C1, NKC, 7>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 8: sa_produce_inline<C1, NKC, 8>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 9: sa_produce_inline<C1, NKC, 9>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 10: sa_produce_inline<C1, NKC, 10>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 11: sa_produce_inline<C1, NKC, 11>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 12: sa_produce_inline<C1, NKC, 12>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 13: sa_produce_inline<C1, NKC, 13>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 14: sa_produce_inline<C1, NKC, 14>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 15: sa_produce_inline<C1, NKC, 15>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 16: sa_produce_inline<C1, NKC, 16>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 17: sa_produce_inline<C1, NKC, 17>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 18: sa_produce_inline<C1, NKC, 18>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 19: sa_produce_inline<C1, NKC, 19>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          case 20: sa_produce_inline<C1, NKC, 20>(p, b, j, i, r, half * NKC, h1, sW0); break;
+          default: break;
         }
         fence_proxy_async_smem();
         mbarrier_arrive(&h1_full[s]);
