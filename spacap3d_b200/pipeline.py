@@ -21,9 +21,9 @@ class GraphedDetector:
 
     def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None):
         assert example.is_cuda
-        # with >= 3 batches in flight the SM-time of FPS matters more than its latency: 4-CTA clusters
+        # FPS cluster size: automatic (8 CTAs of 256 threads, two CTAs per SM) unless overridden
         if fps_cluster is None:
-            fps_cluster = 4 if n_streams >= 3 else 0
+            fps_cluster = 0
         from . import _lib
         _lib.call("spc_set_fps_cluster", int(fps_cluster))
         self.model = model
