@@ -578,9 +578,10 @@ def run_reference(args):
         val = SCENES_PER_GPU * args.steps / s
         config["l2"] = "256 MiB L2 flush between timed steps"
         config["arm"] = ("reference CUDA ops (lib/pointnet2/_ext_src rebuilt unmodified for sm_100a) in the "
-                         "reference op sequence + cuDNN MLP (torch defaults, TF32 conv) + host box decode; 1 GPU")
+                         "reference op sequence + cuDNN MLP (torch defaults, TF32 conv) + host box decode; "
+                         "runs on rank 0 / one GPU only (the other ranks exit)")
         line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 3),
-                "unit": "scenes/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "unit": "scenes/s", "n_gpus": world, "ranks_used": 1, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(s / args.steps * 1e3, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "device": "cuda",
@@ -609,7 +610,7 @@ def run_reference(args):
     val = steps / el
     config["arm"] = "CPU oracle port, batch 1 per step; " + why
     line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 4),
-            "unit": "scenes/s", "n_gpus": 1, "steps": steps, "warmup": min(args.warmup, 1),
+            "unit": "scenes/s", "n_gpus": world, "ranks_used": 1, "steps": steps, "warmup": min(args.warmup, 1),
             "ms_per_step": round(el / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "device": "cpu",
