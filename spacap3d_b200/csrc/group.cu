@@ -132,8 +132,28 @@ __global__ void __launch_bounds__(GP_THREADS) group_points_kernel(
   }
 
   if (VEC4) {
-    // S % 4 == 0 and chunk % 4 == 0: 4 consecutive positions per thread, 16-byte idx load + store
-    for (int t = p0 + tid * 4; t < p1; t += GP_THREADS * 4) {
+    // S % 4 == 0 and chunk % 4 == 0: 4 consecutive positions per thread, 16-byte idx load + store.
+    // The index loads of UNR iterations are issued together: with one CTA per SM (a 160 KB row)
+    // the loop is otherwise bound by the L2 latency of one idx load per thread.
+    constexpr int UNR = 4;
+    int t = p0 + tid * 4;
+    for (; t + (UNR - 1) * GP_THREADS * 4 < p1; t += UNR * GP_THREADS * 4) {
+      int4 i4[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) i4[u] = __ldg(reinterpret_cast<const int4 *>(ix + t + u * GP_THREADS * 4));
+#pragma unroll 2
+      for (int c = 0; c < ct; ++c) {
+        const float *r = STAGED ? s_rows + (size_t)c * N : src + (size_t)c * N;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          float a0, a1, a2, a3;
+          if (STAGED) { a0 = r[i4[u].x]; a1 = r[i4[u].y]; a2 = r[i4[u].z]; a3 = r[i4[u].w]; }
+          else { a0 = __ldg(r + i4[u].x); a1 = __ldg(r + i4[u].y); a2 = __ldg(r + i4[u].z); a3 = __ldg(r + i4[u].w); }
+          st_cs_v4(dst + (size_t)c * S + t + u * GP_THREADS * 4, a0, a1, a2, a3);
+        }
+      }
+    }
+    for (; t < p1; t += GP_THREADS * 4) {
       const int4 i4 = __ldg(reinterpret_cast<const int4 *>(ix + t));
 #pragma unroll 4
       for (int c = 0; c < ct; ++c) {
