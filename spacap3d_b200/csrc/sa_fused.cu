@@ -33,6 +33,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace spc {
@@ -61,7 +63,7 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, unsigned parity) {
 // same, but yields the issue slot between polls (producer / epilogue warps share their SM
 // sub-partitions with each other; a tight spin stole 30 % of the issue slots, ncu)
 __device__ __forceinline__ void mbarrier_wait_relaxed(uint64_t *bar, unsigned parity) {
-  unsigned done;
+  unsigned done, ns = 32;
   for (;;) {
     asm volatile(
         "{\n"
@@ -73,8 +75,9 @@ __device__ __forceinline__ void mbarrier_wait_relaxed(uint64_t *bar, unsigned pa
         : "r"(s2u(bar)), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(40);
-  }
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;          // 32, 64, 128, 256 ns: the stages are double-buffered, so a late
+  }                                  // wake-up costs nothing, a tight spin costs issue slots (25 %, ncu)
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -200,20 +203,28 @@ constexpr int SA_W0_STRIDE = 20;    // floats per channel row of the inline laye
 // In-line layer 0 with exactly NIN inputs: in = [(p-c)/r (3), features (Cf), 1 (bias)], NIN = 4+Cf.
 // Weights sit in shared memory transposed per 8-channel chunk, sW0t[kc][k][8], so that one input
 // updates 8 accumulators from two broadcast 16-byte reads and no FMA is spent on padding.
-template <int C1, int NKC, int NIN>
-__device__ __forceinline__ void sa_produce_inline(const SaFusedParams &p, int b, int j, int i, int r, int kc0,
-                                                  uint8_t *sH1, const float *sW0t) {
-  float in[NIN];
+template <int NIN>
+__device__ __forceinline__ void sa_inline_load(const SaFusedParams &p, int tile, int r, int i, int rows_per_scene,
+                                               float inv_r, float (&in)[NIN]) {
+  const long long R = (long long)tile * SA_ROWS + r;
+  const int b = (int)(R / rows_per_scene);
+  const int j = (int)(R - (long long)b * rows_per_scene) / p.ns;
   const float *pp = p.xyz + ((size_t)b * p.n + i) * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
-  // (p - c) / r, exactly as grouped_xyz -= new_xyz; grouped_xyz /= radius
-  in[0] = __fdiv_rn(__ldg(pp + 0) - __ldg(cc + 0), p.radius);
-  in[1] = __fdiv_rn(__ldg(pp + 1) - __ldg(cc + 1), p.radius);
-  in[2] = __fdiv_rn(__ldg(pp + 2) - __ldg(cc + 2), p.radius);
+  // (p - c) / r as a multiplication by 1/r (this path feeds a bf16 MLP: a 1-ulp difference to the
+  // reference's true division is far below the rounding of the next step)
+  in[0] = (__ldg(pp + 0) - __ldg(cc + 0)) * inv_r;
+  in[1] = (__ldg(pp + 1) - __ldg(cc + 1)) * inv_r;
+  in[2] = (__ldg(pp + 2) - __ldg(cc + 2)) * inv_r;
   const float *fp = p.feat + (size_t)b * p.Cf * p.n + i;
 #pragma unroll
   for (int f = 3; f < NIN - 1; ++f) in[f] = __ldg(fp + (size_t)(f - 3) * p.n);
   in[NIN - 1] = 1.f;                                  // the folded bias rides along as the last "input"
+}
+
+template <int C1, int NKC, int NIN>
+__device__ __forceinline__ void sa_inline_compute(const float (&in)[NIN], int r, int kc0, uint8_t *sH1,
+                                                  const float *sW0t) {
 #pragma unroll 2
   for (int kc = kc0; kc < kc0 + NKC; ++kc) {
     const float4 *w = reinterpret_cast<const float4 *>(sW0t + (size_t)kc * SA_W0_STRIDE * 8);
@@ -425,42 +436,55 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         mbarrier_arrive(&h1_full[s]);
       }
     } else {
+      // lane = row (two threads per row, half of the channels each); the neighbour index is fetched
+      // two tiles ahead and the gathered inputs one tile ahead, so that a tile's math never waits
+      // for its own loads
       const int r = tid & (SA_ROWS - 1);
-      const int half = tid >> 7;                                   // which half of the K chunks
+      const int half = tid >> 7;
       constexpr int NKC = C1 / 16;
-      int i_next = __ldg(p.idx + (long long)blockIdx.x * SA_ROWS + r);
-      for (int k = 0; k < nt; ++k) {
-        const int s = k & 1, n = k >> 1;
-        const int tile = (int)blockIdx.x + k * (int)gridDim.x;
-        const int i = i_next;
-        if (k + 1 < nt) i_next = __ldg(p.idx + (long long)(tile + (int)gridDim.x) * SA_ROWS + r);
-        const long long R = (long long)tile * SA_ROWS + r;
-        const int b = (int)(R / rows_per_scene);
-        const int j = (int)(R - (long long)b * rows_per_scene) / p.ns;
-        mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
-        uint8_t *h1 = sH1 + s * L::H1_BYTES;
-        switch (K0 + 1) {                                          // exact input count (warp-uniform)
-          case 4: sa_produce_inline<C1, NKC, 4>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 5: sa_produce_inline<C1, NKC, 5>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 6: sa_produce_inline<C1, NKC, 6>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 7: sa_produce_inline<C1, NKC, 7>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 8: sa_produce_inline<C1, NKC, 8>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 9: sa_produce_inline<C1, NKC, 9>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 10: sa_produce_inline<C1, NKC, 10>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 11: sa_produce_inline<C1, NKC, 11>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 12: sa_produce_inline<C1, NKC, 12>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 13: sa_produce_inline<C1, NKC, 13>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 14: sa_produce_inline<C1, NKC, 14>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 15: sa_produce_inline<C1, NKC, 15>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 16: sa_produce_inline<C1, NKC, 16>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 17: sa_produce_inline<C1, NKC, 17>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 18: sa_produce_inline<C1, NKC, 18>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 19: sa_produce_inline<C1, NKC, 19>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          case 20: sa_produce_inline<C1, NKC, 20>(p, b, j, i, r, half * NKC, h1, sW0); break;
-          default: break;
+      const float inv_r = 1.0f / p.radius;
+      auto run = [&](auto nin_tag) {
+        constexpr int NIN = decltype(nin_tag)::value;
+        const int t0 = (int)blockIdx.x, dt = (int)gridDim.x;
+        float in_next[NIN];
+        int i1 = __ldg(p.idx + (long long)t0 * SA_ROWS + r);
+        sa_inline_load<NIN>(p, t0, r, i1, rows_per_scene, inv_r, in_next);
+        i1 = nt > 1 ? __ldg(p.idx + (long long)(t0 + dt) * SA_ROWS + r) : 0;
+        for (int k = 0; k < nt; ++k) {
+          const int s = k & 1, n = k >> 1;
+          const int tile = t0 + k * dt;
+          float in[NIN];
+#pragma unroll
+          for (int q = 0; q < NIN; ++q) in[q] = in_next[q];
+          if (k + 1 < nt) {
+            sa_inline_load<NIN>(p, tile + dt, r, i1, rows_per_scene, inv_r, in_next);
+            if (k + 2 < nt) i1 = __ldg(p.idx + (long long)(tile + 2 * dt) * SA_ROWS + r);
+          }
+          mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
+          sa_inline_compute<C1, NKC, NIN>(in, r, half * NKC, sH1 + s * L::H1_BYTES, sW0);
+          fence_proxy_async_smem();
+          mbarrier_arrive(&h1_full[s]);
         }
-        fence_proxy_async_smem();
-        mbarrier_arrive(&h1_full[s]);
+      };
+      switch (K0 + 1) {                                            // exact input count (warp-uniform)
+        case 4: run(std::integral_constant<int, 4>{}); break;
+        case 5: run(std::integral_constant<int, 5>{}); break;
+        case 6: run(std::integral_constant<int, 6>{}); break;
+        case 7: run(std::integral_constant<int, 7>{}); break;
+        case 8: run(std::integral_constant<int, 8>{}); break;
+        case 9: run(std::integral_constant<int, 9>{}); break;
+        case 10: run(std::integral_constant<int, 10>{}); break;
+        case 11: run(std::integral_constant<int, 11>{}); break;
+        case 12: run(std::integral_constant<int, 12>{}); break;
+        case 13: run(std::integral_constant<int, 13>{}); break;
+        case 14: run(std::integral_constant<int, 14>{}); break;
+        case 15: run(std::integral_constant<int, 15>{}); break;
+        case 16: run(std::integral_constant<int, 16>{}); break;
+        case 17: run(std::integral_constant<int, 17>{}); break;
+        case 18: run(std::integral_constant<int, 18>{}); break;
+        case 19: run(std::integral_constant<int, 19>{}); break;
+        case 20: run(std::integral_constant<int, 20>{}); break;
+        default: break;
       }
     }
   } else if (warp == 16) {
