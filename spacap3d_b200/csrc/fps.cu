@@ -289,6 +289,328 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
 // Cost: N*npoint distance evaluations, fully parallel (~10 us for 2048 -> 1024 at B=8) instead
 // of npoint-1 sequential rounds (~290 us).
 // ------------------------------------------------------------------------------------------------
+// ================================================================================================
+// Culled variant for large clouds.
+//
+// After the first few dozen picks a new centre only changes the min-distance of points within the
+// current sampling radius, i.e. of a few per cent of the cloud -- yet the kernel above updates
+// every point every round, and that distance math is 2/3 of its issue slots (which is what limits
+// throughput once several scenes share an SM).  Here the points are first sorted along a Morton
+// curve (fps_morton_sort_kernel), so that the 32*P points of a WARP are spatially compact; each
+// warp keeps the bounding box of its points and its current best candidate.  If the new centre is
+// farther from the box than the warp's largest min-distance, no min-distance in the warp can
+// change (d >= box distance >= every t) and the warp just republishes its cached candidate.
+// The test is conservative w.r.t. fp32 rounding (factor 1-1e-5), so the result is bit-identical.
+// Because points are no longer laid out in the reference's tie-break order, ties are broken
+// explicitly with the virtual index v (one extra redux per level); each thread's slots are sorted
+// by v once at load time so that the strict '>' scan still keeps the lowest v.
+// ================================================================================================
+constexpr int FMS_THREADS = 1024;
+constexpr int FMS_BINS = 32768;       // 32^3 Morton cells
+
+__device__ __forceinline__ unsigned morton_spread5(unsigned x) {   // 5 bits -> every third bit
+  x = (x | (x << 8)) & 0x0000100Fu;
+  x = (x | (x << 4)) & 0x000100C3u;
+  x = (x | (x << 2)) & 0x00011249u;   // bits 0,3,6,9,12
+  return x;
+}
+
+// one CTA per scene: bounding box -> 15-bit Morton cell per point -> counting sort -> perm[b][N]
+__global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const float *__restrict__ xyz, int N,
+                                                                      int32_t *__restrict__ perm) {
+  extern __shared__ int s_cnt[];                 // [FMS_BINS]
+  __shared__ float s_red[6][32];
+  __shared__ float s_box[6];
+  __shared__ int s_part[32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *P = xyz + (size_t)b * N * 3;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int k = tid; k < N; k += FMS_THREADS) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __ldg(P + 3 * k + c);
+      mn[c] = fminf(mn[c], v);
+      mx[c] = fmaxf(mx[c], v);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      mn[c] = fminf(mn[c], __shfl_xor_sync(0xffffffffu, mn[c], o));
+      mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+    }
+    if (lane == 0) { s_red[c][warp] = mn[c]; s_red[3 + c][warp] = mx[c]; }
+  }
+  __syncthreads();
+  if (tid < 3) {
+    float lo = s_red[tid][0], hi = s_red[3 + tid][0];
+    for (int w = 1; w < FMS_THREADS / 32; ++w) { lo = fminf(lo, s_red[tid][w]); hi = fmaxf(hi, s_red[3 + tid][w]); }
+    const float ext = hi - lo;
+    s_box[tid] = lo;
+    s_box[3 + tid] = ext > 0.f ? 32.0f / ext : 0.f;
+  }
+  for (int c = tid; c < FMS_BINS; c += FMS_THREADS) s_cnt[c] = 0;
+  __syncthreads();
+  auto cell_of = [&](int k) {
+    unsigned code = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = (__ldg(P + 3 * k + c) - s_box[c]) * s_box[3 + c];
+      const unsigned q = (unsigned)min(31, max(0, (int)f));
+      code |= morton_spread5(q) << c;
+    }
+    return (int)code;
+  };
+  for (int k = tid; k < N; k += FMS_THREADS) atomicAdd(&s_cnt[cell_of(k)], 1);
+  __syncthreads();
+  constexpr int PER = FMS_BINS / FMS_THREADS;
+  const int c0 = tid * PER;
+  int sum = 0;
+  for (int c = c0; c < c0 + PER; ++c) sum += s_cnt[c];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_part[lane], inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+    s_part[lane] = inc2 - v;
+  }
+  __syncthreads();
+  int run = s_part[warp] + incl - sum;
+  for (int c = c0; c < c0 + PER; ++c) { const int n = s_cnt[c]; s_cnt[c] = run; run += n; }
+  __syncthreads();
+  int32_t *out = perm + (size_t)b * N;
+  for (int k = tid; k < N; k += FMS_THREADS) out[atomicAdd(&s_cnt[cell_of(k)], 1)] = k;
+}
+
+struct __align__(16) FpsCandV {
+  unsigned key, v; int k; float x;
+  float y, z; unsigned pad[2];
+};
+
+__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::
+                   "r"(remote_addr),
+               "r"(a), "r"(b), "r"(remote_bar)
+               : "memory");
+}
+
+template <int P, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_kernel(const FpsParams p,
+                                                                                      const int32_t *__restrict__ perm_all) {
+  constexpr int NW = THREADS / 32;
+  extern __shared__ float s_xyz[];  // [3][P][THREADS] xyz + [P][THREADS] k + [P][THREADS] v
+  float *sx = s_xyz, *sy = s_xyz + P * THREADS, *sz = s_xyz + 2 * P * THREADS;
+  int *sk = reinterpret_cast<int *>(s_xyz + 3 * P * THREADS);
+  unsigned *sv = reinterpret_cast<unsigned *>(s_xyz + 4 * P * THREADS);
+  __shared__ FpsCandV w_cand[2][NW];
+  __shared__ FpsCandV c_cand[2][kMaxCluster];
+  __shared__ __align__(8) uint64_t c_bar[2];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned C = cluster.num_blocks();
+  const unsigned rank = cluster.block_rank();
+  const int scene = blockIdx.y;
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31u, warp = tid >> 5;
+  const float *xyz = p.xyz + (size_t)scene * p.N * 3;
+  const int32_t *perm = perm_all + (size_t)scene * p.N;
+  const unsigned g = rank * THREADS + tid;
+  const unsigned q0 = g * P;                    // first Morton-sorted position owned by this thread
+
+  // ---- load: (v, k) of my slots into smem, insertion-sort them by v, then fetch the coordinates ---
+  int nvalid = 0;
+  for (int s = 0; s < P; ++s) {
+    const unsigned q = q0 + s;
+    unsigned v = 0xffffffffu;
+    int k = 0;
+    if (q < (unsigned)p.N) {
+      k = __ldg(perm + q);
+      const unsigned res = p.log2T ? (__brev((unsigned)k & (unsigned)(p.T - 1)) >> (32 - p.log2T)) : 0u;
+      v = res * (unsigned)p.Q + ((unsigned)k >> p.log2T);      // T is a power of two
+      ++nvalid;
+    }
+    int pos = s;                                                 // insertion sort (ascending v)
+    while (pos > 0 && sv[(pos - 1) * THREADS + tid] > v) {
+      sv[pos * THREADS + tid] = sv[(pos - 1) * THREADS + tid];
+      sk[pos * THREADS + tid] = sk[(pos - 1) * THREADS + tid];
+      --pos;
+    }
+    sv[pos * THREADS + tid] = v;
+    sk[pos * THREADS + tid] = k;
+  }
+  float x[P], y[P], z[P], t[P];
+  float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < P; ++s) {
+    float px = 0.f, py = 0.f, pz = 0.f, pt = -1.0f;
+    if (s < nvalid) {
+      const int k = sk[s * THREADS + tid];
+      px = __ldg(xyz + 3 * k + 0);
+      py = __ldg(xyz + 3 * k + 1);
+      pz = __ldg(xyz + 3 * k + 2);
+      const float mag = __fmaf_rn(pz, pz, __fmaf_rn(px, px, __fmul_rn(py, py)));
+      pt = ((double)mag <= 1e-3) ? -1.0f : 1e10f;   // reference compares in double (F5)
+      if (pt > 0.f) {
+        lox = fminf(lox, px); loy = fminf(loy, py); loz = fminf(loz, pz);
+        hix = fmaxf(hix, px); hiy = fmaxf(hiy, py); hiz = fmaxf(hiz, pz);
+      }
+    }
+    sx[s * THREADS + tid] = px;
+    sy[s * THREADS + tid] = py;
+    sz[s * THREADS + tid] = pz;
+    x[s] = px; y[s] = py; z[s] = pz;
+    t[s] = pt;
+  }
+  // bounding box of the warp's selectable points
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+    loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+    loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+  }
+  const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
+  float ox = p0x, oy = p0y, oz = p0z;
+  int32_t *idx = p.idx + (size_t)scene * p.npoint;
+  float *nxyz = p.new_xyz ? p.new_xyz + (size_t)scene * p.npoint * 3 : nullptr;
+  const bool writer = (rank == 0 && tid == THREADS - 1);
+  if (writer) {
+    idx[0] = 0;
+    if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
+  }
+  const unsigned tx_bytes = 24u * C;
+  uint32_t r_slot0 = 0, r_slot1 = 0, r_bar0 = 0, r_bar1 = 0;
+  if (C > 1) {
+    if (tid == 0) {
+      fps_mbar_init(&c_bar[0], 1);
+      fps_mbar_init(&c_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      fps_mbar_arm(&c_bar[0], tx_bytes);
+      fps_mbar_arm(&c_bar[1], tx_bytes);
+    }
+    cluster.sync();
+    if (warp == 0 && lane < C) {
+      r_slot0 = mapa_cluster(fps_s2u(&c_cand[0][rank]), lane);
+      r_slot1 = mapa_cluster(fps_s2u(&c_cand[1][rank]), lane);
+      r_bar0 = mapa_cluster(fps_s2u(&c_bar[0]), lane);
+      r_bar1 = mapa_cluster(fps_s2u(&c_bar[1]), lane);
+    }
+  } else {
+    __syncthreads();
+  }
+  // the warp's cached candidate (uniform across lanes); key 0 = nothing selectable yet
+  unsigned ck = 0u, cv = 0xffffffffu;
+  int cki = 0;
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  bool fresh = false;                            // the first round must compute
+
+  for (int j = 1; j < p.npoint; ++j) {
+    const int buf = j & 1;
+    // ---- can this centre change any min-distance of the warp? -------------------------------------
+    const float ex = fmaxf(0.f, fmaxf(lox - ox, ox - hix)), ey = fmaxf(0.f, fmaxf(loy - oy, oy - hiy)),
+                ez = fmaxf(0.f, fmaxf(loz - oz, oz - hiz));
+    const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;
+    const bool skip = fresh && (ck == 0u ? !(hix >= lox) : lb2 >= __uint_as_float(ck - 1u));
+    if (!skip) {
+      float best = -1.0f;
+      int bs = 0;
+#pragma unroll
+      for (int s = 0; s < P; ++s) {
+        const float d2 = fminf(sqdist_ref(x[s], y[s], z[s], ox, oy, oz), t[s]);
+        t[s] = d2;
+        if (d2 > best) { best = d2; bs = s; }   // slots are sorted by v: lowest v wins ties
+      }
+      const float mx = sx[bs * THREADS + tid], my = sy[bs * THREADS + tid], mz = sz[bs * THREADS + tid];
+      const int mk = sk[bs * THREADS + tid];
+      const unsigned mv = sv[bs * THREADS + tid];
+      const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
+      ck = __reduce_max_sync(0xffffffffu, key);
+      cv = __reduce_min_sync(0xffffffffu, key == ck ? mv : 0xffffffffu);
+      const unsigned src = __reduce_min_sync(0xffffffffu, (key == ck && mv == cv) ? lane : 32u);
+      cki = __shfl_sync(0xffffffffu, mk, src);
+      cx = __shfl_sync(0xffffffffu, mx, src);
+      cy = __shfl_sync(0xffffffffu, my, src);
+      cz = __shfl_sync(0xffffffffu, mz, src);
+      fresh = true;
+    }
+    if (lane == 0) {
+      FpsCandV *e = &w_cand[buf][warp];
+      *reinterpret_cast<uint4 *>(e) = make_uint4(ck, cv, (unsigned)cki, __float_as_uint(cx));
+      e->y = cy; e->z = cz;
+    }
+    __syncthreads();
+    // ---- CTA arg-max: largest key, then smallest v ------------------------------------------------
+    uint4 e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
+    float ey2 = 0.f, ez2 = 0.f;
+    if (lane < NW) {
+      e4 = *reinterpret_cast<const uint4 *>(&w_cand[buf][lane]);
+      ey2 = w_cand[buf][lane].y; ez2 = w_cand[buf][lane].z;
+    }
+    unsigned bmax = __reduce_max_sync(0xffffffffu, e4.x);
+    unsigned bv = __reduce_min_sync(0xffffffffu, (lane < NW && e4.x == bmax) ? e4.y : 0xffffffffu);
+    unsigned src = __reduce_min_sync(0xffffffffu, (lane < NW && e4.x == bmax && e4.y == bv) ? lane : 32u);
+    unsigned wk = __shfl_sync(0xffffffffu, e4.z, src);
+    unsigned wxb = __shfl_sync(0xffffffffu, e4.w, src);
+    float wy = __shfl_sync(0xffffffffu, ey2, src);
+    float wz = __shfl_sync(0xffffffffu, ez2, src);
+    if (C > 1) {
+      if (warp == 0 && lane < C) {
+        const uint32_t rs = buf ? r_slot1 : r_slot0, rb = buf ? r_bar1 : r_bar0;
+        st_async_v4(rs, bmax, bv, wk, wxb, rb);
+        st_async_v2(rs + 16, __float_as_uint(wy), __float_as_uint(wz), rb);
+      }
+      fps_mbar_wait(&c_bar[buf], (unsigned)((j - 1) >> 1) & 1u);
+      if (tid == 0) fps_mbar_arm(&c_bar[buf], tx_bytes);
+      e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
+      ey2 = 0.f; ez2 = 0.f;
+      if (lane < C) {
+        e4 = *reinterpret_cast<const uint4 *>(&c_cand[buf][lane]);
+        ey2 = c_cand[buf][lane].y; ez2 = c_cand[buf][lane].z;
+      }
+      bmax = __reduce_max_sync(0xffffffffu, e4.x);
+      bv = __reduce_min_sync(0xffffffffu, (lane < C && e4.x == bmax) ? e4.y : 0xffffffffu);
+      src = __reduce_min_sync(0xffffffffu, (lane < C && e4.x == bmax && e4.y == bv) ? lane : 32u);
+      wk = __shfl_sync(0xffffffffu, e4.z, src);
+      wxb = __shfl_sync(0xffffffffu, e4.w, src);
+      wy = __shfl_sync(0xffffffffu, ey2, src);
+      wz = __shfl_sync(0xffffffffu, ez2, src);
+    }
+    int old = 0;
+    if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
+    else { ox = __uint_as_float(wxb); oy = wy; oz = wz; old = (int)wk; }
+    if (writer) {
+      idx[j] = old;
+      if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
+    }
+  }
+  if (C > 1) cluster.sync();
+}
+
+template <int P, int THREADS>
+static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
+  auto kern = fps_cull_kernel<P, THREADS>;
+  const size_t smem = (size_t)5 * P * THREADS * sizeof(float);
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, B, 1);
+  cfg.blockDim = dim3(THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SPC_CUDA(cudaLaunchKernelEx(&cfg, kern, p, perm));
+  return SPC_OK;
+}
+
 __global__ void fps_fill_kernel(int *p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -446,8 +768,8 @@ extern "C" int spc_set_fps_cluster(int cluster_ctas) {
 }
 
 extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
-  (void)N;
-  return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B) * 4;
+  // D (B,npoint) + ok (B) for the ordered-prefix proof, perm (B,N) for the Morton-sorted (culled) kernel
+  return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B + (size_t)B * (size_t)(N > 0 ? N : 0)) * 4;
 }
 
 extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint,
@@ -521,6 +843,25 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
     return SPC_ERR_UNSUPPORTED;
   }
   while (C > 1 && need <= 1) { C /= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
+  // ---- Morton-sorted, culled kernel: needs the caller's workspace (perm) ----------------------------
+  if (workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && N >= 8192 && npoint >= 64 &&
+      B <= 65535 && !getenv("SPC_FPS_NOCULL")) {
+    const int need256 = (int)(((long long)N + (long long)C * 256 - 1) / ((long long)C * 256));
+    if (need256 <= 20) {
+      int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
+      const size_t sort_smem = (size_t)FMS_BINS * sizeof(int);
+      SPC_CUDA(cudaFuncSetAttribute(fps_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+      fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(xyz, N, perm);
+      SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
+      const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;
+      switch (P256) {
+        case 8: return launch_fps_cull<8, 256>(p, perm, B, C, stream);
+        case 10: return launch_fps_cull<10, 256>(p, perm, B, C, stream);
+        case 16: return launch_fps_cull<16, 256>(p, perm, B, C, stream);
+        default: return launch_fps_cull<20, 256>(p, perm, B, C, stream);
+      }
+    }
+  }
   // 256-thread CTAs with 20 points per thread and TWO CTAs per SM whenever the cloud fits: fewer
   // warps per reduction level make a round faster (1.32 vs 1.51 ms for 40k -> 2048 at batch 8) and
   // two latency-bound CTAs (of different scenes / batches) share one SM's issue slots, which halves
