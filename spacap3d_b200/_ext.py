@@ -37,6 +37,11 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# clouds at least this large get a workspace, which lets the library use its Morton-sorted, culled
+# FPS kernel (fps.cu); the result is identical either way
+FPS_WORKSPACE_MIN_N = 8192
+
+
 def furthest_point_sampling(points, nsamples):
     """(B,N,3) f32 -> (B,nsamples) i32.   sampling.cpp:66-87"""
     _check(points, "points", torch.float32)
@@ -44,8 +49,14 @@ def furthest_point_sampling(points, nsamples):
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
-        _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
-                  out.data_ptr(), None, _stream())
+        if N >= FPS_WORKSPACE_MIN_N and nsamples >= 2:
+            nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
+            _lib.call("spc_furthest_point_sampling_ex", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), None, 0, ws.data_ptr(), nbytes, _stream())
+        else:
+            _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), None, _stream())
     return out
 
 
@@ -63,11 +74,12 @@ def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False):
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     new_xyz = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device)
     with torch.cuda.device(points.device):
-        if hint_ordered and 2 <= nsamples <= N:
+        if (hint_ordered and 2 <= nsamples <= N) or (N >= FPS_WORKSPACE_MIN_N and nsamples >= 2):
             nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
             _lib.call("spc_furthest_point_sampling_ex", points.data_ptr(), B, N, int(nsamples),
-                      out.data_ptr(), new_xyz.data_ptr(), 1, ws.data_ptr(), nbytes, _stream())
+                      out.data_ptr(), new_xyz.data_ptr(), int(bool(hint_ordered)), ws.data_ptr(), nbytes,
+                      _stream())
         else:
             _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), new_xyz.data_ptr(), _stream())

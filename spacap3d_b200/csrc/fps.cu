@@ -275,20 +275,6 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
   if (C > 1) cluster.sync();  // no CTA may exit while a peer can still store into its smem
 }
 
-// ------------------------------------------------------------------------------------------------
-// "Verify in parallel what would be constructed sequentially".
-// SA2..SA4 of the detector run FPS on the OUTPUT of the previous FPS (an FPS-ordered point list),
-// where the answer is 0..npoint-1 unless exact distance ties interfere (SURVEY F10: the reference
-// model silently relies on this).  Whether FPS(xyz)[0:npoint] == identity can be CHECKED with no
-// sequential dependency: with the first j points selected, point j must be the unique maximum of
-// the running min-distance among all not-yet-selected points.  Kernel A computes
-// D[j] = min_{i<j} d(p_j, p_i) (what round j's winner scored); kernel B recomputes every point's
-// running min-distance and flags any k > j that reaches D[j] (a tie or a larger value -- then
-// the tie-break / order decides and the full kernel must run).  Same fp32 arithmetic as the
-// sequential kernel (sqdist_ref, fminf, temp = 1e10), so the proof is exact, not approximate.
-// Cost: N*npoint distance evaluations, fully parallel (~10 us for 2048 -> 1024 at B=8) instead
-// of npoint-1 sequential rounds (~290 us).
-// ------------------------------------------------------------------------------------------------
 // ================================================================================================
 // Culled variant for large clouds.
 //
@@ -310,12 +296,18 @@ constexpr int FMS_BINS = 32768;       // 32^3 Morton cells
 
 __device__ __forceinline__ unsigned morton_spread5(unsigned x) {   // 5 bits -> every third bit
   x = (x | (x << 8)) & 0x0000100Fu;
-  x = (x | (x << 4)) & 0x000100C3u;
-  x = (x | (x << 2)) & 0x00011249u;   // bits 0,3,6,9,12
+  x = (x | (x << 4)) & 0x000010C3u;
+  x = (x | (x << 2)) & 0x00001249u;   // bits 0,3,6,9,12
   return x;
 }
 
-// one CTA per scene: bounding box -> 15-bit Morton cell per point -> counting sort -> perm[b][N]
+// one CTA per scene: bounding box -> 15-bit Morton cell per point -> counting sort -> perm[b][N].
+// N <= FMS_THREADS * FMS_ITEMS (the culled kernel's own capacity); every thread keeps the cell codes of
+// its <= 40 points in registers (two per register) between the counting and the scatter pass, and
+// loads are issued eight points at a time so that the three passes are not latency-bound.
+constexpr int FMS_ITEMS = 40;
+constexpr int FMS_BATCH = 8;
+
 __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const float *__restrict__ xyz, int N,
                                                                       int32_t *__restrict__ perm) {
   extern __shared__ int s_cnt[];                 // [FMS_BINS]
@@ -324,14 +316,21 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
   __shared__ int s_part[32];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float *P = xyz + (size_t)b * N * 3;
+  for (int c = tid; c < FMS_BINS; c += FMS_THREADS) s_cnt[c] = 0;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int k = tid; k < N; k += FMS_THREADS) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float v = __ldg(P + 3 * k + c);
-      mn[c] = fminf(mn[c], v);
-      mx[c] = fmaxf(mx[c], v);
+  for (int i0 = 0; i0 < FMS_ITEMS; i0 += FMS_BATCH) {
+    float v[FMS_BATCH][3];
+#pragma unroll
+    for (int i = 0; i < FMS_BATCH; ++i) {
+      const int k = tid + (i0 + i) * FMS_THREADS;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[i][c] = k < N ? __ldg(P + 3 * k + c) : NAN;   // NaN: ignored by fmin/fmax
     }
+#pragma unroll
+    for (int i = 0; i < FMS_BATCH; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { mn[c] = fminf(mn[c], v[i][c]); mx[c] = fmaxf(mx[c], v[i][c]); }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -348,25 +347,37 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
     for (int w = 1; w < FMS_THREADS / 32; ++w) { lo = fminf(lo, s_red[tid][w]); hi = fmaxf(hi, s_red[3 + tid][w]); }
     const float ext = hi - lo;
     s_box[tid] = lo;
-    s_box[3 + tid] = ext > 0.f ? 32.0f / ext : 0.f;
+    s_box[3 + tid] = (ext > 0.f && ext < INFINITY) ? 32.0f / ext : 0.f;
   }
-  for (int c = tid; c < FMS_BINS; c += FMS_THREADS) s_cnt[c] = 0;
   __syncthreads();
-  auto cell_of = [&](int k) {
-    unsigned code = 0;
+  const float bx = s_box[0], by = s_box[1], bz = s_box[2], gx = s_box[3], gy = s_box[4], gz = s_box[5];
+  unsigned codes[FMS_ITEMS / 2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float f = (__ldg(P + 3 * k + c) - s_box[c]) * s_box[3 + c];
-      const unsigned q = (unsigned)min(31, max(0, (int)f));
-      code |= morton_spread5(q) << c;
+  for (int i0 = 0; i0 < FMS_ITEMS; i0 += FMS_BATCH) {
+    float v[FMS_BATCH][3];
+#pragma unroll
+    for (int i = 0; i < FMS_BATCH; ++i) {
+      const int k = tid + (i0 + i) * FMS_THREADS;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[i][c] = k < N ? __ldg(P + 3 * k + c) : 0.f;
     }
-    return (int)code;
-  };
-  for (int k = tid; k < N; k += FMS_THREADS) atomicAdd(&s_cnt[cell_of(k)], 1);
+#pragma unroll
+    for (int i = 0; i < FMS_BATCH; ++i) {
+      const int k = tid + (i0 + i) * FMS_THREADS;
+      const unsigned qx = (unsigned)min(31, max(0, (int)((v[i][0] - bx) * gx)));
+      const unsigned qy = (unsigned)min(31, max(0, (int)((v[i][1] - by) * gy)));
+      const unsigned qz = (unsigned)min(31, max(0, (int)((v[i][2] - bz) * gz)));
+      const unsigned code = morton_spread5(qx) | (morton_spread5(qy) << 1) | (morton_spread5(qz) << 2);
+      if (k < N) atomicAdd(&s_cnt[code], 1);
+      if ((i & 1) == 0) codes[(i0 + i) >> 1] = code;
+      else codes[(i0 + i) >> 1] |= code << 16;
+    }
+  }
   __syncthreads();
   constexpr int PER = FMS_BINS / FMS_THREADS;
   const int c0 = tid * PER;
   int sum = 0;
+#pragma unroll 8
   for (int c = c0; c < c0 + PER; ++c) sum += s_cnt[c];
   int incl = sum;
 #pragma unroll
@@ -381,10 +392,16 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
   }
   __syncthreads();
   int run = s_part[warp] + incl - sum;
+#pragma unroll 8
   for (int c = c0; c < c0 + PER; ++c) { const int n = s_cnt[c]; s_cnt[c] = run; run += n; }
   __syncthreads();
   int32_t *out = perm + (size_t)b * N;
-  for (int k = tid; k < N; k += FMS_THREADS) out[atomicAdd(&s_cnt[cell_of(k)], 1)] = k;
+#pragma unroll
+  for (int i = 0; i < FMS_ITEMS; ++i) {
+    const int k = tid + i * FMS_THREADS;
+    const unsigned code = (codes[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+    if (k < N) out[atomicAdd(&s_cnt[code], 1)] = k;
+  }
 }
 
 struct __align__(16) FpsCandV {
@@ -397,6 +414,13 @@ __device__ __forceinline__ void st_async_v2(uint32_t remote_addr, uint32_t a, ui
                    "r"(remote_addr),
                "r"(a), "r"(b), "r"(remote_bar)
                : "memory");
+}
+
+// Several lanes hold the maximal key: the smallest virtual index wins.  Deliberately NOT inlined: ptxas
+// otherwise if-converts the rare path into predicated redux that sit on every round's dependency chain.
+__device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned lane) {
+  const unsigned vmin = __reduce_min_sync(0xffffffffu, hit ? v : 0xffffffffu);
+  return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
 }
 
 template <int P, int THREADS>
@@ -421,6 +445,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
   const int32_t *perm = perm_all + (size_t)scene * p.N;
   const unsigned g = rank * THREADS + tid;
   const unsigned q0 = g * P;                    // first Morton-sorted position owned by this thread
+  if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {   // verified shortcut, as in fps_cluster_kernel
+    int32_t *oidx = p.idx + (size_t)scene * p.npoint;
+    for (unsigned j = g; j < (unsigned)p.npoint; j += C * THREADS) oidx[j] = (int)j;
+    if (p.new_xyz) {
+      float *o = p.new_xyz + (size_t)scene * p.npoint * 3;
+      for (unsigned e = g; e < 3u * (unsigned)p.npoint; e += C * THREADS) o[e] = __ldg(xyz + e);
+    }
+    return;
+  }
 
   // ---- load: (v, k) of my slots into smem, insertion-sort them by v, then fetch the coordinates ---
   int nvalid = 0;
@@ -502,61 +535,94 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
   } else {
     __syncthreads();
   }
-  // the warp's cached candidate (uniform across lanes); key 0 = nothing selectable yet
-  unsigned ck = 0u, cv = 0xffffffffu;
-  int cki = 0;
-  float cx = 0.f, cy = 0.f, cz = 0.f;
+  // The warp's candidate lives in w_cand (both buffers once it is stable); only its key is kept in a
+  // register for the cull test.  key 0 = nothing selectable.
+  unsigned ck = 0u;
   bool fresh = false;                            // the first round must compute
+  bool stale = false;                            // the OTHER buffer still holds an older candidate
+  int my_k = -1;                                 // point index of the warp's candidate
+  int old = -2;                                  // the last pick
+
+  // arg-max over the lanes holding (key, v): largest key, then smallest v.  The common case (a unique
+  // maximum) costs two dependent redux; the ballot that detects ties issues alongside the second.
+  auto argmax_lane = [&](bool valid, unsigned key, unsigned v, unsigned &kmax) -> unsigned {
+    kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
+    const bool hit = valid && key == kmax;
+    unsigned src = __reduce_min_sync(0xffffffffu, hit ? lane : 32u);
+    const unsigned ties = __ballot_sync(0xffffffffu, hit);
+    if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fps_resolve_tie(hit, v, lane);   // rare
+    return src & 31u;
+  };
 
   for (int j = 1; j < p.npoint; ++j) {
     const int buf = j & 1;
     // ---- can this centre change any min-distance of the warp? -------------------------------------
-    const float ex = fmaxf(0.f, fmaxf(lox - ox, ox - hix)), ey = fmaxf(0.f, fmaxf(loy - oy, oy - hiy)),
-                ez = fmaxf(0.f, fmaxf(loz - oz, oz - hiz));
-    const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;
-    const bool skip = fresh && (ck == 0u ? !(hix >= lox) : lb2 >= __uint_as_float(ck - 1u));
+    // (the warp whose own candidate was just picked certainly must update: no test on the critical path)
+    bool skip = false;
+    if (fresh && old != my_k) {
+      const float ex = fmaxf(0.f, fmaxf(lox - ox, ox - hix)), ey = fmaxf(0.f, fmaxf(loy - oy, oy - hiy)),
+                  ez = fmaxf(0.f, fmaxf(loz - oz, oz - hiz));
+      const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;
+      skip = ck == 0u ? !(hix >= lox) : lb2 >= __uint_as_float(ck - 1u);
+    }
     if (!skip) {
-      float best = -1.0f;
-      int bs = 0;
+      float bvv[P];
+      int bsi[P];
 #pragma unroll
       for (int s = 0; s < P; ++s) {
         const float d2 = fminf(sqdist_ref(x[s], y[s], z[s], ox, oy, oz), t[s]);
         t[s] = d2;
-        if (d2 > best) { best = d2; bs = s; }   // slots are sorted by v: lowest v wins ties
+        bvv[s] = d2;
+        bsi[s] = s;
       }
+      // tournament over the slots (depth log2 P instead of a P-long dependent chain); the left operand
+      // always covers the lower slots, so strict '>' keeps the lowest slot (= lowest v) among equals
+#pragma unroll
+      for (int stride = 1; stride < P; stride *= 2) {
+#pragma unroll
+        for (int s = 0; s + stride < P; s += 2 * stride) {
+          if (bvv[s + stride] > bvv[s]) { bvv[s] = bvv[s + stride]; bsi[s] = bsi[s + stride]; }
+        }
+      }
+      const float best = bvv[0];
+      const int bs = bsi[0];
       const float mx = sx[bs * THREADS + tid], my = sy[bs * THREADS + tid], mz = sz[bs * THREADS + tid];
       const int mk = sk[bs * THREADS + tid];
       const unsigned mv = sv[bs * THREADS + tid];
       const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-      ck = __reduce_max_sync(0xffffffffu, key);
-      cv = __reduce_min_sync(0xffffffffu, key == ck ? mv : 0xffffffffu);
-      const unsigned src = __reduce_min_sync(0xffffffffu, (key == ck && mv == cv) ? lane : 32u);
-      cki = __shfl_sync(0xffffffffu, mk, src);
-      cx = __shfl_sync(0xffffffffu, mx, src);
-      cy = __shfl_sync(0xffffffffu, my, src);
-      cz = __shfl_sync(0xffffffffu, mz, src);
+      const unsigned wsrc = argmax_lane(true, key, mv, ck);
+      if (lane == wsrc) {
+        FpsCandV *e = &w_cand[buf][warp];
+        *reinterpret_cast<uint4 *>(e) = make_uint4(ck, mv, (unsigned)mk, __float_as_uint(mx));
+        *reinterpret_cast<float2 *>(&e->y) = make_float2(my, mz);
+      }
+      my_k = ck ? __shfl_sync(0xffffffffu, mk, wsrc) : -1;   // consumed next round only
       fresh = true;
-    }
-    if (lane == 0) {
-      FpsCandV *e = &w_cand[buf][warp];
-      *reinterpret_cast<uint4 *>(e) = make_uint4(ck, cv, (unsigned)cki, __float_as_uint(cx));
-      e->y = cy; e->z = cz;
+      stale = true;
+    } else if (stale) {
+      if (lane == 0) {
+        const FpsCandV *src = &w_cand[buf ^ 1][warp];
+        FpsCandV *dst = &w_cand[buf][warp];
+        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
+        *reinterpret_cast<float2 *>(&dst->y) = *reinterpret_cast<const float2 *>(&src->y);
+      }
+      stale = false;
     }
     __syncthreads();
-    // ---- CTA arg-max: largest key, then smallest v ------------------------------------------------
+    // ---- CTA arg-max, computed redundantly by every warp ------------------------------------------
     uint4 e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-    float ey2 = 0.f, ez2 = 0.f;
+    float2 eyz = make_float2(0.f, 0.f);
     if (lane < NW) {
       e4 = *reinterpret_cast<const uint4 *>(&w_cand[buf][lane]);
-      ey2 = w_cand[buf][lane].y; ez2 = w_cand[buf][lane].z;
+      eyz = *reinterpret_cast<const float2 *>(&w_cand[buf][lane].y);
     }
-    unsigned bmax = __reduce_max_sync(0xffffffffu, e4.x);
-    unsigned bv = __reduce_min_sync(0xffffffffu, (lane < NW && e4.x == bmax) ? e4.y : 0xffffffffu);
-    unsigned src = __reduce_min_sync(0xffffffffu, (lane < NW && e4.x == bmax && e4.y == bv) ? lane : 32u);
+    unsigned bmax;
+    unsigned src = argmax_lane(lane < NW, e4.x, e4.y, bmax);
+    unsigned bv = __shfl_sync(0xffffffffu, e4.y, src);
     unsigned wk = __shfl_sync(0xffffffffu, e4.z, src);
     unsigned wxb = __shfl_sync(0xffffffffu, e4.w, src);
-    float wy = __shfl_sync(0xffffffffu, ey2, src);
-    float wz = __shfl_sync(0xffffffffu, ez2, src);
+    float wy = __shfl_sync(0xffffffffu, eyz.x, src);
+    float wz = __shfl_sync(0xffffffffu, eyz.y, src);
     if (C > 1) {
       if (warp == 0 && lane < C) {
         const uint32_t rs = buf ? r_slot1 : r_slot0, rb = buf ? r_bar1 : r_bar0;
@@ -566,20 +632,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
       fps_mbar_wait(&c_bar[buf], (unsigned)((j - 1) >> 1) & 1u);
       if (tid == 0) fps_mbar_arm(&c_bar[buf], tx_bytes);
       e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-      ey2 = 0.f; ez2 = 0.f;
+      eyz = make_float2(0.f, 0.f);
       if (lane < C) {
         e4 = *reinterpret_cast<const uint4 *>(&c_cand[buf][lane]);
-        ey2 = c_cand[buf][lane].y; ez2 = c_cand[buf][lane].z;
+        eyz = *reinterpret_cast<const float2 *>(&c_cand[buf][lane].y);
       }
-      bmax = __reduce_max_sync(0xffffffffu, e4.x);
-      bv = __reduce_min_sync(0xffffffffu, (lane < C && e4.x == bmax) ? e4.y : 0xffffffffu);
-      src = __reduce_min_sync(0xffffffffu, (lane < C && e4.x == bmax && e4.y == bv) ? lane : 32u);
+      src = argmax_lane(lane < C, e4.x, e4.y, bmax);
       wk = __shfl_sync(0xffffffffu, e4.z, src);
       wxb = __shfl_sync(0xffffffffu, e4.w, src);
-      wy = __shfl_sync(0xffffffffu, ey2, src);
-      wz = __shfl_sync(0xffffffffu, ez2, src);
+      wy = __shfl_sync(0xffffffffu, eyz.x, src);
+      wz = __shfl_sync(0xffffffffu, eyz.y, src);
     }
-    int old = 0;
+    old = 0;
     if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
     else { ox = __uint_as_float(wxb); oy = wy; oz = wz; old = (int)wk; }
     if (writer) {
@@ -594,7 +658,11 @@ template <int P, int THREADS>
 static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
   auto kern = fps_cull_kernel<P, THREADS>;
   const size_t smem = (size_t)5 * P * THREADS * sizeof(float);
-  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;   // per instantiation; the attribute is sticky for the process
+  if (!attr_set) {
+    SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C, B, 1);
   cfg.blockDim = dim3(THREADS, 1, 1);
@@ -611,6 +679,20 @@ static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C
   return SPC_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// "Verify in parallel what would be constructed sequentially".
+// SA2..SA4 of the detector run FPS on the OUTPUT of the previous FPS (an FPS-ordered point list),
+// where the answer is 0..npoint-1 unless exact distance ties interfere (SURVEY F10: the reference
+// model silently relies on this).  Whether FPS(xyz)[0:npoint] == identity can be CHECKED with no
+// sequential dependency: with the first j points selected, point j must be the unique maximum of
+// the running min-distance among all not-yet-selected points.  Kernel A computes
+// D[j] = min_{i<j} d(p_j, p_i) (what round j's winner scored); kernel B recomputes every point's
+// running min-distance and flags any k > j that reaches D[j] (a tie or a larger value -- then
+// the tie-break / order decides and the full kernel must run).  Same fp32 arithmetic as the
+// sequential kernel (sqdist_ref, fminf, temp = 1e10), so the proof is exact, not approximate.
+// Cost: N*npoint distance evaluations, fully parallel (~10 us for 2048 -> 1024 at B=8) instead
+// of npoint-1 sequential rounds (~290 us).
+// ------------------------------------------------------------------------------------------------
 __global__ void fps_fill_kernel(int *p, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -767,6 +849,21 @@ extern "C" int spc_set_fps_cluster(int cluster_ctas) {
   return SPC_OK;
 }
 
+// process-wide switch for the Morton-sorted, culled kernel (0 = off, 1 = on).  Measured on B200, batch
+// 8 x 40 000 -> 2048: one call alone is ~15 % slower with it (0.67 vs 0.60 us per round: the explicit
+// tie-break and the cull test sit on the round's dependency chain, and the sort prepass is extra), but it
+// issues a fraction of the instructions, so a pipeline that keeps several batches in flight on different
+// streams gains ~5 % overall.  spacap3d_b200/pipeline.py turns it on; SPC_FPS_CULL=0/1 overrides.
+static int g_fps_cull = 0;
+extern "C" int spc_set_fps_cull(int on) {
+  if (on != 0 && on != 1) {
+    set_error("spc_set_fps_cull: %d is not 0 or 1", on);
+    return SPC_ERR_INVALID_ARG;
+  }
+  g_fps_cull = on;
+  return SPC_OK;
+}
+
 extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
   // D (B,npoint) + ok (B) for the ordered-prefix proof, perm (B,N) for the Morton-sorted (culled) kernel
   return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B + (size_t)B * (size_t)(N > 0 ? N : 0)) * 4;
@@ -782,6 +879,11 @@ extern "C" int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, in
                                               void *workspace, size_t workspace_bytes,
                                               void *stream_) {
   return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, workspace, workspace_bytes, stream_);
+}
+
+static bool fps_cull_enabled() {
+  if (const char *e = getenv("SPC_FPS_CULL")) return atoi(e) != 0;
+  return g_fps_cull != 0;
 }
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
@@ -845,12 +947,16 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   while (C > 1 && need <= 1) { C /= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
   // ---- Morton-sorted, culled kernel: needs the caller's workspace (perm) ----------------------------
   if (workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && N >= 8192 && npoint >= 64 &&
-      B <= 65535 && !getenv("SPC_FPS_NOCULL")) {
+      B <= 65535 && C <= 8 && fps_cull_enabled()) {
     const int need256 = (int)(((long long)N + (long long)C * 256 - 1) / ((long long)C * 256));
-    if (need256 <= 20) {
+    if (need256 <= 20 && N <= FMS_THREADS * FMS_ITEMS) {
       int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
       const size_t sort_smem = (size_t)FMS_BINS * sizeof(int);
-      SPC_CUDA(cudaFuncSetAttribute(fps_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+      static bool sort_attr_set = false;
+      if (!sort_attr_set) {
+        SPC_CUDA(cudaFuncSetAttribute(fps_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+        sort_attr_set = true;
+      }
       fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(xyz, N, perm);
       SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
       const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;

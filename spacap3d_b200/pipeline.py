@@ -19,13 +19,16 @@ class GraphedDetector:
     replays the graph and (optionally) copies the requested outputs to pinned host buffers; it
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
-    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None):
+    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None,
+                 fps_cull=True):
         assert example.is_cuda
         # FPS cluster size: automatic (8 CTAs of 256 threads, two CTAs per SM) unless overridden
         if fps_cluster is None:
             fps_cluster = 0
         from . import _lib
         _lib.call("spc_set_fps_cluster", int(fps_cluster))
+        # several batches in flight: the culled FPS kernel trades single-call latency for issue slots
+        _lib.call("spc_set_fps_cull", int(bool(fps_cull)))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)

@@ -71,6 +71,44 @@ def fps_cases():
     return c
 
 
+def fps_large_cases():
+    """Clouds large enough (N >= 8192) for the library's Morton-sorted, culled FPS kernel; checked against
+    the oracle (itself pinned on fps_cases) rather than against stored reference outputs."""
+    c = {}
+    rng = np.random.default_rng(202)
+    # exact ties everywhere: 24^3 lattice, forwards and reversed
+    lat = _lattice(24, 0.25, 2.875)
+    c["lattice_13824"] = (np.stack([lat, lat[::-1].copy()], 0), 700)
+    # heavy duplication: 700 distinct points resampled to 16384, npoint beyond #distinct
+    base = rng.uniform(-3, 3, (2, 700, 3)).astype(np.float32)
+    pick = rng.integers(0, 700, (2, 16384))
+    c["dup_16384"] = (np.ascontiguousarray(np.take_along_axis(base, pick[..., None].repeat(3, -1), 1)), 1024)
+    # near-origin skip inside a large cloud, first point itself skipped in scene 0
+    near = rng.uniform(-0.02, 0.02, (2, 10000, 3)).astype(np.float32)
+    far = rng.uniform(-2, 2, (2, 10000, 3)).astype(np.float32)
+    mix = np.where(rng.random((2, 10000, 1)) < 0.3, near, far).astype(np.float32)
+    mix[0, 0] = [0.001, -0.002, 0.0005]
+    c["origin_mix_10000"] = (np.ascontiguousarray(mix), 600)
+    # size edges of the culled kernel: smallest N, largest N of an 8x256x20 cluster, one past it
+    c["n8192"] = (rng.uniform(-3, 3, (1, 8192, 3)).astype(np.float32), 300)
+    c["n40960"] = (rng.uniform(-4, 4, (1, 40960, 3)).astype(np.float32), 512)
+    c["n40961"] = (rng.uniform(-4, 4, (1, 40961, 3)).astype(np.float32), 256)
+    # degenerate extents: all points on a plane / on a line / identical
+    plane = rng.uniform(-3, 3, (1, 9000, 3)).astype(np.float32)
+    plane[..., 2] = 1.5
+    line = np.zeros((1, 9000, 3), np.float32)
+    line[..., 0] = rng.uniform(-5, 5, (1, 9000)).astype(np.float32)
+    line[..., 1] = 0.25
+    c["plane_line_9000"] = (np.concatenate([plane, line], 0), 400)
+    c["identical_8500"] = (np.full((1, 8500, 3), 0.75, np.float32), 70)
+    # clustered (very non-uniform density) cloud
+    cen = rng.uniform(-4, 4, (1, 12, 3))
+    which = rng.integers(0, 12, (1, 20000))
+    pts = np.take_along_axis(cen, which[..., None].repeat(3, -1), 1) + rng.normal(0, 0.05, (1, 20000, 3))
+    c["clusters_20000"] = (pts.astype(np.float32), 1024)
+    return c
+
+
 def fps_follow_on(xyz, idx, npoint):
     """new_xyz gathered with idx, as the SA module does (pointnet2_modules.py:240-242)."""
     return np.take_along_axis(xyz, idx[..., None].astype(np.int64).repeat(3, -1), 1)[:, :npoint]
