@@ -284,7 +284,9 @@ def run_ours(args):
         # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
         from spacap3d_b200.pipeline import GraphedDetector
         runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS)
-        _lib.call("spc_set_fps_cluster", 0)      # the knob is baked into the captured graphs; eager passes stay automatic
+        # the knobs are baked into the captured graphs; eager passes stay on the single-call defaults
+        _lib.call("spc_set_fps_cluster", 0)
+        _lib.call("spc_set_fps_cull", 0)
 
         def timed_graph(submit, steps, warmup, sampler=None):
             for i in range(warmup):
@@ -391,13 +393,21 @@ def run_ours(args):
                     "avg_launch_us": round(avg_ms * 1e3, 2), "algo_bytes_per_launch": int(avg_bytes),
                     "share_of_step": round(d["ms"] / prof_steps / eager["ms_per_step"], 4),
                     "share_of": "eager single-stream step (kernels of different batches overlap in graph mode)"}
-    fps = agg.get("spc_furthest_point_sampling")
+    # the sequential sampler of the raw cloud (SA1): args = (xyz, B, N, npoint, ...); the later FPS calls
+    # run on FPS-ordered inputs and mostly take the verified shortcut, so they are not "rounds"
+    fps_recs = [r for r in meter.records if r[0] in ("spc_furthest_point_sampling", "spc_furthest_point_sampling_ex")]
     latency_bound = None
-    if fps:
-        rounds = sum(max(r[4][3] - 1, 0) for r in meter.records if r[0] == "spc_furthest_point_sampling")
-        latency_bound = {"kernel": "furthest_point_sampling", "ms_per_step": round(fps["ms"] / prof_steps, 4),
-                         "us_per_round": round(fps["ms"] * 1e3 / max(rounds, 1), 4),
-                         "sequential_rounds_per_step": rounds // prof_steps}
+    if fps_recs:
+        n_max = max(r[4][2] for r in fps_recs)
+        big = [r for r in fps_recs if r[4][2] == n_max]
+        ms = sum(r[2].elapsed_time(r[3]) for r in big)
+        rounds = sum(max(r[4][3] - 1, 0) for r in big)
+        latency_bound = {"kernel": "furthest_point_sampling (N=%d -> %d)" % (n_max, big[0][4][3]),
+                         "ms_per_step": round(ms / prof_steps, 4),
+                         "us_per_round": round(ms * 1e3 / max(rounds, 1), 4),
+                         "sequential_rounds_per_step": rounds // prof_steps,
+                         "note": "latency-bound by construction (each round depends on the previous pick); "
+                                 "timed with the single-call kernel (culling off)"}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

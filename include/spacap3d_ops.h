@@ -103,6 +103,16 @@ int spc_group_points(const float *points, const int32_t *idx, int B, int C, int 
  * grad_out (B,C,npoint,nsample), idx (B,npoint,nsample) -> grad_points (B,C,N) */
 int spc_group_points_grad(const float *grad_out, const int32_t *idx, int B, int C, int N,
                           int npoint, int nsample, float *grad_points, void *stream);
+/* Same result (up to fp32 summation order), atomic-free: with a workspace of
+ * spc_group_points_grad_workspace_bytes(B,N,npoint,nsample) bytes the index tensor is inverted once into
+ * per-point position lists shared by all C channels and every output element is summed by one thread
+ * (or one warp) from grad_out rows staged in shared memory.  Bit-reproducible from run to run when
+ * npoint*nsample <= 49152; the reference's RED.ADD order is not.  Falls back to the
+ * entry above when workspace is NULL/too small or C < 4. */
+size_t spc_group_points_grad_workspace_bytes(int B, int N, int npoint, int nsample);
+int spc_group_points_grad_ex(const float *grad_out, const int32_t *idx, int B, int C, int N,
+                             int npoint, int nsample, float *grad_points, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* three_nn(unknowns, knows)                              interpolate.cpp:14-40, interpolate_gpu.cu:9-68
  * unknown (B,n,3), known (B,m,3) -> dist2 (B,n,3) SQUARED distances ascending, idx (B,n,3).

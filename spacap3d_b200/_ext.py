@@ -155,8 +155,14 @@ def group_points_grad(grad_out, idx, n):
     B, C, npoint, nsample = grad_out.shape
     out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        _lib.call("spc_group_points_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(n),
-                  npoint, nsample, out.data_ptr(), _stream())
+        nbytes = _lib.load().spc_group_points_grad_workspace_bytes(B, int(n), npoint, nsample) if C >= 4 else 0
+        if nbytes:
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=grad_out.device)
+            _lib.call("spc_group_points_grad_ex", grad_out.data_ptr(), idx.data_ptr(), B, C, int(n),
+                      npoint, nsample, out.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        else:
+            _lib.call("spc_group_points_grad", grad_out.data_ptr(), idx.data_ptr(), B, C, int(n),
+                      npoint, nsample, out.data_ptr(), _stream())
     return out
 
 

@@ -27,6 +27,7 @@ SIGNATURES = {
     "spc_ball_query_ex": [_p, _p, _i, _i, _i, _f, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_group_points": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "spc_group_points_grad_ex": [_p, _p, _i, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
     "spc_three_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "spc_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
@@ -62,6 +63,8 @@ def load():
                        (lib.spc_abi_version(), ABI_VERSION))
     lib.spc_ball_query_workspace_bytes.argtypes = [_i, _i]
     lib.spc_ball_query_workspace_bytes.restype = ctypes.c_size_t
+    lib.spc_group_points_grad_workspace_bytes.argtypes = [_i, _i, _i, _i]
+    lib.spc_group_points_grad_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_fps_workspace_bytes.argtypes = [_i, _i, _i]
     lib.spc_fps_workspace_bytes.restype = ctypes.c_size_t
     for name, argtypes in SIGNATURES.items():

@@ -279,6 +279,261 @@ static GroupPlan plan_group(int B, int C, int N, int S, bool backward) {
   return g;
 }
 
+// ----------------------------------------------------------------------------------------------
+// group_points backward, atomic-free formulation (used when the caller provides a workspace)
+// ----------------------------------------------------------------------------------------------
+// Shared-memory fp32 atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN), and the ball-query
+// padding makes a few low-index points the target of a large share of all positions, so the
+// accumulator kernel above runs at 2-6 % of HBM bandwidth.  Here the index tensor is inverted once
+// per call into a CSR list (point -> positions that reference it, ascending) that all C channels
+// share, and the scatter becomes a gather:
+//    grad_points[b,c,i] = sum over t in list(b,i) of grad_out[b,c,t]
+// A CTA stages CT rows of grad_out (one position partition of <= 24576 floats each) in shared memory
+// with one bulk-TMA copy, then every thread sums the short lists of its points from shared memory and
+// whole warps share the long ones (lane-strided + butterfly).  No floating-point atomics, coalesced
+// 16-bit list reads, and the summation order is fixed by the list => bit-reproducible results when
+// the position range fits one or two partitions (two partial sums commute); with more partitions the
+// <= H partial sums per element are combined with global RED in arbitrary order.
+constexpr int GG_THREADS = 512;
+constexpr int GG_PART_MAX = 24576;   // positions per partition: 96 KB of fp32 => two CTAs per SM
+constexpr int GG_CT_MAX = 4;
+constexpr int GG_SHORT = 32;         // lists up to this length are summed by one thread
+constexpr int GG_LONG_CAP = 2048;    // long lists per CTA handled warp-wide (overflow: one thread each)
+
+struct GradPlan {
+  int H, Sp, CT, Np;
+  bool lists_smem;
+  size_t smem;
+};
+
+static GradPlan plan_group_grad(int C, int N, int S) {
+  GradPlan g;
+  g.H = ceil_div(S, GG_PART_MAX);
+  g.Sp = ((ceil_div(S, g.H) + 7) / 8) * 8;     // multiples of 8 keep the uint16 lists 16-byte aligned
+  g.H = ceil_div(S, g.Sp);
+  g.Np = ((N + 1 + 3) / 4) * 4;                // offsets row stride (16-byte aligned rows)
+  int ct = (int)((64 * 1024) / ((size_t)g.Sp * sizeof(float)));
+  g.CT = max(1, min(min(ct, GG_CT_MAX), C));
+  const size_t rows = (size_t)g.CT * g.Sp * sizeof(float);
+  const size_t lists = (size_t)g.Sp * sizeof(uint16_t) + (size_t)g.Np * sizeof(int);
+  g.lists_smem = rows + lists <= 112 * 1024;   // still two CTAs per SM
+  g.smem = rows + (g.lists_smem ? lists : 0);
+  return g;
+}
+
+// counts[b][h][1 + idx[b,t]] += 1   (offsets row = Np ints per (b,h), slot 0 stays 0)
+__global__ void gg_hist_kernel(const int32_t *__restrict__ idx, int N, int S, int Sp, int H, int Np,
+                               int *__restrict__ offsets) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= S) return;
+  const int i = __ldg(idx + (size_t)b * S + t);
+  if ((unsigned)i < (unsigned)N) atomicAdd(offsets + ((size_t)b * H + t / Sp) * Np + 1 + i, 1);
+}
+
+// in-place inclusive scan of offsets[b][h][1..N]  (one CTA per (b,h))
+__global__ void __launch_bounds__(1024) gg_scan_kernel(int N, int Np, int *__restrict__ offsets) {
+  __shared__ int s_part[32];
+  int *row = offsets + (size_t)blockIdx.x * Np + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (N + 1023) / 1024;
+  const int e0 = min(N, tid * per), e1 = min(N, e0 + per);
+  int sum = 0;
+  for (int e = e0; e < e1; ++e) sum += row[e];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_part[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int v = s_part[lane];
+    int inc2 = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+    s_part[lane] = inc2 - v;
+  }
+  __syncthreads();
+  int run = s_part[warp] + incl - sum;
+  for (int e = e0; e < e1; ++e) { run += row[e]; row[e] = run; }
+}
+
+// Deterministic fill: a warp owns 32 consecutive points and scans every position of its partition in
+// ascending order, so each list comes out sorted by position without any atomics on the cursors.
+// The partition's indices are staged in shared memory once per CTA (8 warps = 256 points).
+constexpr int GG_FILL_WARPS = 8;
+__global__ void __launch_bounds__(GG_FILL_WARPS * 32) gg_fill_kernel(const int32_t *__restrict__ idx, int N, int S,
+                                                                      int Sp, int H, int Np,
+                                                                      const int *__restrict__ offsets,
+                                                                      uint16_t *__restrict__ order) {
+  extern __shared__ __align__(128) int s_idx[];     // [Sp]
+  __shared__ int s_cur[GG_FILL_WARPS][32];
+  __shared__ __align__(8) uint64_t bar;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p0 = h * Sp, len = min(S, p0 + Sp) - p0;
+  const int32_t *ix = idx + (size_t)b * S + p0;
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(ix) & 15) == 0) && (len % 4 == 0);
+  if (bulk_ok) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, (unsigned)(len * sizeof(int)));
+      bulk_g2s(s_idx, ix, (unsigned)(len * sizeof(int)), &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int e = tid; e < len; e += GG_FILL_WARPS * 32) s_idx[e] = __ldg(ix + e);
+    __syncthreads();
+  }
+  const int i0 = (blockIdx.x * GG_FILL_WARPS + warp) * 32;
+  if (i0 >= N) return;
+  const int *off = offsets + ((size_t)b * H + h) * Np;
+  s_cur[warp][lane] = (i0 + lane < N) ? off[i0 + lane] : 0;
+  __syncwarp();
+  uint16_t *ord = order + (size_t)b * S + p0;
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    const int t = t0 + lane;
+    const int v = t < len ? s_idx[t] : -1;
+    const unsigned rel = (unsigned)(v - i0);
+    const bool hit = v >= 0 && rel < 32u && v < N;
+    if (!__any_sync(0xffffffffu, hit)) continue;
+    const unsigned peers = __match_any_sync(0xffffffffu, hit ? rel : 32u + (unsigned)lane);
+    int base = 0;
+    if (hit) base = s_cur[warp][rel];
+    __syncwarp();
+    if (hit) {
+      const unsigned before = peers & ((1u << lane) - 1u);
+      ord[base + __popc(before)] = (uint16_t)t;
+      if (before == 0u) s_cur[warp][rel] = base + __popc(peers);
+    }
+    __syncwarp();
+  }
+}
+
+template <int CT, bool LISTS_SMEM>
+__global__ void __launch_bounds__(GG_THREADS) group_points_grad_csr_kernel(
+    const float *__restrict__ grad_out, const int *__restrict__ offsets, const uint16_t *__restrict__ order,
+    int C, int N, int S, int Sp, int H, int Np, float *__restrict__ grad_points) {
+  extern __shared__ __align__(128) float s_rows[];   // [CT][Sp] (+ uint16 [Sp] lists + int [Np] offsets)
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_long[GG_LONG_CAP];
+  __shared__ int s_nlong;
+  const int b = blockIdx.z, h = blockIdx.x;
+  const int c0 = blockIdx.y * CT;
+  const int ct = min(CT, C - c0);
+  const int p0 = h * Sp;
+  const int len = min(S, p0 + Sp) - p0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float *g = grad_out + ((size_t)b * C + c0) * S + p0;
+  const int *off_g = offsets + ((size_t)b * H + h) * Np;
+  const uint16_t *ord_g = order + (size_t)b * S + p0;
+  uint16_t *s_ord = reinterpret_cast<uint16_t *>(s_rows + (size_t)CT * Sp);
+  int *s_off = reinterpret_cast<int *>(s_ord + Sp);
+  if (tid == 0) s_nlong = 0;
+  // ---- stage ct partial rows (row r at s_rows + r*Sp) and, if they fit, the lists --------------------
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && (S % 8 == 0) && (len % 8 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(ord_g) & 15) == 0) && ((reinterpret_cast<uintptr_t>(off_g) & 15) == 0);
+  if (bulk_ok) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned bytes = (unsigned)(ct * len * sizeof(float));
+      if (LISTS_SMEM) bytes += (unsigned)(len * sizeof(uint16_t) + Np * sizeof(int));
+      mbar_expect_tx(&bar, bytes);
+      if (LISTS_SMEM) {       // lists first: they are needed first and come from L2
+        bulk_g2s(s_off, off_g, (unsigned)(Np * sizeof(int)), &bar);
+        bulk_g2s(s_ord, ord_g, (unsigned)(len * sizeof(uint16_t)), &bar);
+      }
+      for (int r = 0; r < ct; ++r) bulk_g2s(s_rows + (size_t)r * Sp, g + (size_t)r * S, (unsigned)(len * sizeof(float)), &bar);
+    }
+    mbar_wait(&bar, 0);
+  } else {
+    for (int r = 0; r < ct; ++r)
+      for (int e = tid; e < len; e += GG_THREADS) s_rows[(size_t)r * Sp + e] = __ldg(g + (size_t)r * S + e);
+    if (LISTS_SMEM) {
+      for (int e = tid; e < len; e += GG_THREADS) s_ord[e] = ord_g[e];
+      for (int e = tid; e <= N; e += GG_THREADS) s_off[e] = off_g[e];
+    }
+    __syncthreads();
+  }
+  const int *off = LISTS_SMEM ? s_off : off_g;
+  const uint16_t *ord = LISTS_SMEM ? s_ord : ord_g;
+  float *dst = grad_points + ((size_t)b * C + c0) * N;
+  // ---- short lists: one thread per point ----------------------------------------------------------
+  for (int i = tid; i < N; i += GG_THREADS) {
+    const int o0 = off[i], o1 = off[i + 1];
+    if (o1 - o0 > GG_SHORT) {
+      const int q = atomicAdd(&s_nlong, 1);
+      if (q < GG_LONG_CAP) { s_long[q] = i; continue; }
+    }
+    float acc[CT];
+#pragma unroll
+    for (int r = 0; r < CT; ++r) acc[r] = 0.f;
+    int k = o0;
+    for (; k + 4 <= o1; k += 4) {
+      const int q0 = ord[k], q1 = ord[k + 1], q2 = ord[k + 2], q3 = ord[k + 3];
+#pragma unroll
+      for (int r = 0; r < CT; ++r) {
+        const float *row = s_rows + (size_t)r * Sp;
+        acc[r] = ((acc[r] + row[q0]) + row[q1]) + row[q2];
+        acc[r] += row[q3];
+      }
+    }
+    for (; k < o1; ++k) {
+      const int q0 = ord[k];
+#pragma unroll
+      for (int r = 0; r < CT; ++r) acc[r] += s_rows[(size_t)r * Sp + q0];
+    }
+#pragma unroll
+    for (int r = 0; r < CT; ++r) {
+      if (r < ct) {
+        if (H == 1) dst[(size_t)r * N + i] = acc[r];
+        else if (acc[r] != 0.f) atomicAdd(dst + (size_t)r * N + i, acc[r]);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- long lists: one warp per point ---------------------------------------------------------------
+  const int nlong = min(s_nlong, GG_LONG_CAP);
+  for (int q = warp; q < nlong; q += GG_THREADS / 32) {
+    const int i = s_long[q];
+    const int o0 = off[i], o1 = off[i + 1];
+    float acc[CT];
+#pragma unroll
+    for (int r = 0; r < CT; ++r) acc[r] = 0.f;
+    for (int k = o0 + lane; k < o1; k += 32) {
+      const int qq = ord[k];
+#pragma unroll
+      for (int r = 0; r < CT; ++r) acc[r] += s_rows[(size_t)r * Sp + qq];
+    }
+#pragma unroll
+    for (int r = 0; r < CT; ++r)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < CT; ++r) {
+        if (r < ct) {
+          if (H == 1) dst[(size_t)r * N + i] = acc[r];
+          else if (acc[r] != 0.f) atomicAdd(dst + (size_t)r * N + i, acc[r]);
+        }
+      }
+    }
+  }
+}
+
+template <int CT, bool LISTS_SMEM>
+static int launch_group_grad_csr(const float *grad_out, const int *offsets, const uint16_t *order, int B, int C,
+                                 int N, int S, const GradPlan &g, float *grad_points, cudaStream_t stream) {
+  auto kern = group_points_grad_csr_kernel<CT, LISTS_SMEM>;
+  if (g.smem > 40 * 1024)
+    SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+  dim3 grid(g.H, ceil_div(C, CT), B);
+  kern<<<grid, GG_THREADS, g.smem, stream>>>(grad_out, offsets, order, C, N, S, g.Sp, g.H, g.Np, grad_points);
+  SPC_LAUNCH_CHECK("group_points_grad_csr_kernel");
+  return SPC_OK;
+}
+
 }  // namespace spc
 
 using namespace spc;
@@ -372,4 +627,56 @@ extern "C" int spc_group_points_grad(const float *grad_out, const int32_t *idx, 
   }
   SPC_LAUNCH_CHECK("group_points_grad_kernel");
   return SPC_OK;
+}
+
+extern "C" size_t spc_group_points_grad_workspace_bytes(int B, int N, int npoint, int nsample) {
+  if (B <= 0 || N <= 0 || npoint <= 0 || nsample <= 0) return 0;
+  const long long S = (long long)npoint * nsample;
+  if (S >= (1LL << 31)) return 0;
+  const GradPlan g = plan_group_grad(1, N, (int)S);
+  // offsets (B,H,Np) int32  +  order (B,S) uint16, both starting 16-byte aligned
+  return (size_t)B * g.H * (size_t)g.Np * sizeof(int) + (((size_t)B * (size_t)S * sizeof(uint16_t) + 15) & ~(size_t)15);
+}
+
+extern "C" int spc_group_points_grad_ex(const float *grad_out, const int32_t *idx, int B, int C, int N, int npoint,
+                                        int nsample, float *grad_points, void *workspace, size_t workspace_bytes,
+                                        void *stream_) {
+  SPC_CHECK_ARG(B >= 0 && C >= 0 && N >= 0 && npoint >= 0 && nsample >= 0, "group_points_grad: bad sizes");
+  const long long S64 = (long long)npoint * nsample;
+  SPC_CHECK_ARG(S64 < (1LL << 31), "group_points_grad: npoint*nsample overflows int32");
+  const int S = (int)S64;
+  const size_t need = spc_group_points_grad_workspace_bytes(B, N, npoint, nsample);
+  // The list build costs ~N*S/1024 warp-iterations per scene and is shared by all C channels: worth it
+  // once C is a few channels and the cloud is not huge relative to C (SA2-SA4, vote aggregation,
+  // multiview SA1); otherwise the atomic kernel is faster.
+  if (!workspace || need == 0 || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) || C < 4 ||
+      (long long)N > 512LL * C || B == 0 || B > 65535 || getenv("SPC_GROUP_GRAD_ATOMIC"))
+    return spc_group_points_grad(grad_out, idx, B, C, N, npoint, nsample, grad_points, stream_);
+  SPC_CHECK_ARG(grad_points && grad_out && idx, "group_points_grad: null pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const GradPlan g = plan_group_grad(C, N, S);
+  SPC_CHECK_ARG(ceil_div(C, g.CT) <= 65535 && g.H <= 65535, "group_points_grad: grid too large");
+  int *offsets = reinterpret_cast<int *>(workspace);
+  const size_t off_bytes = (size_t)B * g.H * (size_t)g.Np * sizeof(int);
+  uint16_t *order = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(workspace) + off_bytes);
+  SPC_CUDA(cudaMemsetAsync(offsets, 0, off_bytes, stream));
+  gg_hist_kernel<<<dim3(ceil_div(S, 256), B), 256, 0, stream>>>(idx, N, S, g.Sp, g.H, g.Np, offsets);
+  gg_scan_kernel<<<B * g.H, 1024, 0, stream>>>(N, g.Np, offsets);
+  const size_t fill_smem = (size_t)g.Sp * sizeof(int);
+  SPC_CUDA(cudaFuncSetAttribute(gg_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+  gg_fill_kernel<<<dim3(ceil_div(N, 32 * GG_FILL_WARPS), g.H, B), GG_FILL_WARPS * 32, fill_smem, stream>>>(
+      idx, N, S, g.Sp, g.H, g.Np, offsets, order);
+  SPC_LAUNCH_CHECK("group_points_grad list build");
+  if (g.H > 1) SPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), stream));
+#define GG_CASE(ct)                                                                                              \
+  case ct:                                                                                                       \
+    return g.lists_smem ? launch_group_grad_csr<ct, true>(grad_out, offsets, order, B, C, N, S, g, grad_points, stream) \
+                        : launch_group_grad_csr<ct, false>(grad_out, offsets, order, B, C, N, S, g, grad_points, stream);
+  switch (g.CT) {
+    GG_CASE(1) GG_CASE(2) GG_CASE(3)
+    default:
+      return g.lists_smem ? launch_group_grad_csr<4, true>(grad_out, offsets, order, B, C, N, S, g, grad_points, stream)
+                          : launch_group_grad_csr<4, false>(grad_out, offsets, order, B, C, N, S, g, grad_points, stream);
+  }
+#undef GG_CASE
 }

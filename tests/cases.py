@@ -206,6 +206,26 @@ def group_cases():
     return c
 
 
+def group_grad_big_cases():
+    """name -> (idx (B,np,ns), C, N): shapes that take the list-based (atomic-free) backward."""
+    rng = np.random.default_rng(515)
+    c = {}
+
+    def padded(B, N, npoint, ns, fill):
+        idx = rng.integers(0, N, (B, npoint, ns)).astype(np.int32)
+        cnt = rng.integers(1, ns + 1, (B, npoint, 1))
+        first = np.minimum(idx[:, :, :1], fill)            # hubs: low indices collect the padding
+        return np.where(np.arange(ns)[None, None, :] < cnt, idx, first).astype(np.int32)
+
+    c["sa2_like_two_partitions"] = (padded(2, 2048, 1024, 32, 40), 9, 2048)       # S=32768 -> H=2, CT=1
+    c["sa3_like"] = (padded(2, 1024, 512, 16, 25), 10, 1024)                      # S=8192  -> H=1, CT=2
+    c["sa4_like_ct4"] = (padded(3, 512, 256, 16, 10), 7, 512)                     # S=4096  -> CT=4, C%4 != 0
+    c["three_partitions"] = (padded(1, 3000, 1000, 60, 100), 4, 3000)             # S=60000 -> H=3
+    c["odd_unaligned"] = (padded(2, 333, 77, 13, 5), 5, 333)                      # S=1001: no bulk copy
+    c["one_hub"] = (np.zeros((1, 64, 16), np.int32) + 7, 6, 50)                   # every position -> point 7
+    return c
+
+
 def interp_cases():
     """name -> (points (B,C,m), idx (B,n,3), weight (B,n,3))"""
     rng = np.random.default_rng(606)

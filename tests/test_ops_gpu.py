@@ -158,6 +158,26 @@ def test_group(ext, ref_ext, name):
         np.testing.assert_allclose(gg, rg, rtol=1e-5, atol=1e-5 * np.abs(want).max())
 
 
+@pytest.mark.parametrize("name", list(cases.group_grad_big_cases().keys()))
+def test_group_grad_list_based(ext, ref_ext, name, monkeypatch):
+    """The atomic-free backward (per-point position lists): equals the oracle within fp32 summation
+    error, equals the atomic kernel, and is bit-reproducible when the positions fit two partitions."""
+    idx, C, N = cases.group_grad_big_cases()[name]
+    B, npoint, ns = idx.shape
+    g = cases.grad_for("group_grad_big/" + name, (B, C, npoint, ns))
+    want = oracle.group_points_grad(g, idx, N)
+    tol = dict(rtol=1e-5, atol=2e-5 * np.abs(want).max())
+    got = ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy()
+    np.testing.assert_allclose(got, want, **tol)
+    if npoint * ns <= 49152:
+        for _ in range(3):
+            np.testing.assert_array_equal(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), got)
+    monkeypatch.setenv("SPC_GROUP_GRAD_ATOMIC", "1")
+    np.testing.assert_allclose(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), want, **tol)
+    if ref_ext is not None:
+        np.testing.assert_allclose(ref_ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), want, **tol)
+
+
 @pytest.mark.parametrize("name", list(cases.interp_cases().keys()))
 def test_interpolate(ext, ref_ext, name):
     pts, idx, w = cases.interp_cases()[name]
