@@ -934,14 +934,14 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   if (g_fps_cluster) C = g_fps_cluster;
   if (const char *e = getenv("SPC_FPS_CLUSTER")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
   int need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512));
-  while (need > 32 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
+  while (need > 27 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
   if (C == 16 && cached_max16 < 0) cached_max16 = max_active_clusters<6, 512, true>(16);
   if (C == 16 && cached_max16 <= 0) {
     set_error("fps: N=%d needs a 16-CTA cluster which this device cannot schedule", N);
     return SPC_ERR_UNSUPPORTED;
   }
-  if (need > 32) {
-    set_error("fps: N=%d exceeds the on-chip capacity of a 16-CTA cluster (max %d points)", N, 16 * 512 * 32);
+  if (need > 27) {
+    set_error("fps: N=%d exceeds the on-chip capacity of a 16-CTA cluster (max %d points)", N, 16 * 512 * 27);
     return SPC_ERR_UNSUPPORTED;
   }
   while (C > 1 && need <= 1) { C /= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
@@ -983,13 +983,14 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
       }
     }
   }
-  static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 32};
-  int P = 32;
+  // P = 27 is the most that fits: 4 arrays x 27 x 512 x 4 B = 216 KB of the 227 KB a CTA may use
+  static const int opts[] = {2, 3, 4, 5, 6, 8, 10, 12, 16, 20, 24, 27};
+  int P = 27;
   for (int o : opts) if (o >= need) { P = o; break; }
   switch (P) {
     FPS_CASE(2, 512, true) FPS_CASE(3, 512, true) FPS_CASE(4, 512, true) FPS_CASE(5, 512, true)
     FPS_CASE(6, 512, true) FPS_CASE(8, 512, true) FPS_CASE(10, 512, true) FPS_CASE(12, 512, true)
-    FPS_CASE(16, 512, true) FPS_CASE(20, 512, true) FPS_CASE(24, 512, false) FPS_CASE(32, 512, false)
+    FPS_CASE(16, 512, true) FPS_CASE(20, 512, true) FPS_CASE(24, 512, false) FPS_CASE(27, 512, false)
   }
   set_error("fps: internal dispatch error");
   return SPC_ERR_UNSUPPORTED;

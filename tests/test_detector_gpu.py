@@ -127,3 +127,36 @@ def test_detector_backbone_and_votes_fast_vs_fp32():
     assert (off_f - off_r).abs().max().item() <= 3e-2 * off_r.abs().max().item()
     for k in ("objectness_scores", "center", "bbox_corner", "sem_cls_scores", "aggregated_vote_inds"):
         assert fast[k].shape == ref[k].shape and torch.isfinite(fast[k].double()).all()
+
+
+def test_graphed_pipeline_equals_eager():
+    """CUDA-graph replay on several streams (incl. the culled FPS kernel it switches on) returns exactly
+    what the eager forward returns, batch after batch."""
+    from spacap3d_b200 import _lib
+    from spacap3d_b200.detector import VoteNetDetector
+    from spacap3d_b200.pipeline import GraphedDetector
+    from spacap3d_b200.scenes import make_scene
+    torch.manual_seed(0)
+    model = VoteNetDetector(input_feature_dim=1).to(DEV).eval()
+    _randomize_bn(model, 5)
+    batches = [torch.from_numpy(np.stack([make_scene(200 + 2 * i, 20000), make_scene(201 + 2 * i, 20000)], 0)).to(DEV)
+               for i in range(4)]
+    keys = ("sa1_inds", "seed_inds", "vote_xyz", "aggregated_vote_inds", "objectness_scores", "center",
+            "sem_cls_scores", "bbox_corner")
+    with torch.no_grad():
+        want = [{k: model({"point_clouds": b})[k].clone() for k in keys} for b in batches]
+    try:
+        runner = GraphedDetector(model, batches[0], n_streams=3, result_keys=keys)
+        for rep in range(2):
+            slots = [runner.submit(b) for b in batches[:3]]
+            for s, w in zip(slots, want[:3]):
+                runner.wait(s)
+                for k in keys:
+                    assert torch.equal(runner.outputs[s][k], w[k]), (rep, k)
+            s = runner.submit(batches[3], to_host=True)
+            host = runner.wait(s)
+            for k in keys:
+                assert torch.equal(host[k], want[3][k].cpu()), k
+    finally:
+        _lib.call("spc_set_fps_cull", 0)
+        _lib.call("spc_set_fps_cluster", 0)

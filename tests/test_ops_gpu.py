@@ -73,6 +73,16 @@ def test_fps_culled_every_cluster_size(ext, cluster):
     np.testing.assert_array_equal(got, want)
 
 
+def test_fps_config5_200k_points(ext):
+    """BASELINE config 5's largest cloud: 200 000 points -> 8192 samples (a 16-CTA cluster), one scene."""
+    from spacap3d_b200.scenes import make_scene_xyz
+    xyz = make_scene_xyz(77, 200000)[None]
+    want = oracle.furthest_point_sampling(xyz, 8192)
+    got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), 8192)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, 8192))
+
+
 def test_fps_culled_scene_40k(ext):
     """The BASELINE shape through the culled kernel (the path the graph pipeline uses)."""
     from spacap3d_b200 import _lib
