@@ -60,6 +60,17 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu capture of this round (bench.py cannot run under a profiler); None when the file is missing."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_%s_traffic.json" % tag)
+    try:
+        with open(path) as f:
+            return int(json.load(f)["dram_bytes_per_launch_avg"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -388,7 +399,9 @@ def run_ours(args):
                     "unit": "TFLOP/s" if tensor_bound else "GB/s",
                     "frac": round(achieved / (tf_peak if tensor_bound else hbm_peak), 4),
                     "algo_flops_per_launch": int(avg_flops),
-                    "traffic": None, "peak_source": peak_src,
+                    "traffic": ncu_traffic("sa_fused"), "traffic_source": "profiles/r1_sa_fused_traffic.json (ncu --set full, "
+                    "dram read+write per launch, mean of the step's %d launches)" % (d["launches"] // prof_steps),
+                    "peak_source": peak_src,
                     "launches_per_step": d["launches"] // prof_steps,
                     "avg_launch_us": round(avg_ms * 1e3, 2), "algo_bytes_per_launch": int(avg_bytes),
                     "share_of_step": round(d["ms"] / prof_steps / eager["ms_per_step"], 4),

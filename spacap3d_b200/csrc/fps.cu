@@ -423,14 +423,25 @@ __device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned 
   return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
 }
 
-template <int P, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_kernel(const FpsParams p,
-                                                                                      const int32_t *__restrict__ perm_all) {
+// XYZ_SMEM = false: coordinates and min-distances in registers (128 regs, 100 KB smem: two CTAs per SM).
+// XYZ_SMEM = true : only the min-distances stay in registers; coordinates are read from shared memory by
+//   the (few) warps that are not culled, point indices are kept as uint16 and the tie-break index is
+//   recomputed from them => <= 80 regs and 70 KB smem: THREE CTAs per SM, i.e. a scene occupies 2.7 SMs
+//   instead of 4 for the duration of the call.
+template <int P, int THREADS, bool XYZ_SMEM>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (XYZ_SMEM ? 3 : 2) : 1))
+fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
   constexpr int NW = THREADS / 32;
-  extern __shared__ float s_xyz[];  // [3][P][THREADS] xyz + [P][THREADS] k + [P][THREADS] v
+  extern __shared__ float s_xyz[];  // [3][P][THREADS] xyz + ([P][THREADS] k + [P][THREADS] v | [P][THREADS] k16)
   float *sx = s_xyz, *sy = s_xyz + P * THREADS, *sz = s_xyz + 2 * P * THREADS;
-  int *sk = reinterpret_cast<int *>(s_xyz + 3 * P * THREADS);
-  unsigned *sv = reinterpret_cast<unsigned *>(s_xyz + 4 * P * THREADS);
+  // during the load-time sort the XYZ_SMEM variant borrows the (not yet written) x / y planes for v / k
+  int *sk = XYZ_SMEM ? reinterpret_cast<int *>(sy) : reinterpret_cast<int *>(s_xyz + 3 * P * THREADS);
+  unsigned *sv = XYZ_SMEM ? reinterpret_cast<unsigned *>(sx) : reinterpret_cast<unsigned *>(s_xyz + 4 * P * THREADS);
+  uint16_t *sk16 = reinterpret_cast<uint16_t *>(s_xyz + 3 * P * THREADS);
+  auto v_of_k = [&](unsigned k) -> unsigned {
+    const unsigned res = p.log2T ? (__brev(k & (unsigned)(p.T - 1)) >> (32 - p.log2T)) : 0u;
+    return res * (unsigned)p.Q + (k >> p.log2T);      // T is a power of two
+  };
   __shared__ FpsCandV w_cand[2][NW];
   __shared__ FpsCandV c_cand[2][kMaxCluster];
   __shared__ __align__(8) uint64_t c_bar[2];
@@ -463,8 +474,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
     int k = 0;
     if (q < (unsigned)p.N) {
       k = __ldg(perm + q);
-      const unsigned res = p.log2T ? (__brev((unsigned)k & (unsigned)(p.T - 1)) >> (32 - p.log2T)) : 0u;
-      v = res * (unsigned)p.Q + ((unsigned)k >> p.log2T);      // T is a power of two
+      v = v_of_k((unsigned)k);
       ++nvalid;
     }
     int pos = s;                                                 // insertion sort (ascending v)
@@ -477,12 +487,15 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
     sk[pos * THREADS + tid] = k;
   }
   float x[P], y[P], z[P], t[P];
+  int kk[P];
+#pragma unroll
+  for (int s = 0; s < P; ++s) kk[s] = sk[s * THREADS + tid];   // before the planes are overwritten
   float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
 #pragma unroll
   for (int s = 0; s < P; ++s) {
     float px = 0.f, py = 0.f, pz = 0.f, pt = -1.0f;
     if (s < nvalid) {
-      const int k = sk[s * THREADS + tid];
+      const int k = kk[s];
       px = __ldg(xyz + 3 * k + 0);
       py = __ldg(xyz + 3 * k + 1);
       pz = __ldg(xyz + 3 * k + 2);
@@ -496,6 +509,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
     sx[s * THREADS + tid] = px;
     sy[s * THREADS + tid] = py;
     sz[s * THREADS + tid] = pz;
+    if (XYZ_SMEM) sk16[s * THREADS + tid] = (uint16_t)kk[s];
     x[s] = px; y[s] = py; z[s] = pz;
     t[s] = pt;
   }
@@ -570,7 +584,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
       int bsi[P];
 #pragma unroll
       for (int s = 0; s < P; ++s) {
-        const float d2 = fminf(sqdist_ref(x[s], y[s], z[s], ox, oy, oz), t[s]);
+        const float d2 = XYZ_SMEM ? fminf(sqdist_ref(sx[s * THREADS + tid], sy[s * THREADS + tid],
+                                                     sz[s * THREADS + tid], ox, oy, oz), t[s])
+                                  : fminf(sqdist_ref(x[s], y[s], z[s], ox, oy, oz), t[s]);
         t[s] = d2;
         bvv[s] = d2;
         bsi[s] = s;
@@ -587,8 +603,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
       const float best = bvv[0];
       const int bs = bsi[0];
       const float mx = sx[bs * THREADS + tid], my = sy[bs * THREADS + tid], mz = sz[bs * THREADS + tid];
-      const int mk = sk[bs * THREADS + tid];
-      const unsigned mv = sv[bs * THREADS + tid];
+      const int mk = XYZ_SMEM ? (int)sk16[bs * THREADS + tid] : sk[bs * THREADS + tid];
+      const unsigned mv = XYZ_SMEM ? v_of_k((unsigned)mk) : sv[bs * THREADS + tid];
       const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
       const unsigned wsrc = argmax_lane(true, key, mv, ck);
       if (lane == wsrc) {
@@ -654,10 +670,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cull_ke
   if (C > 1) cluster.sync();
 }
 
-template <int P, int THREADS>
+template <int P, int THREADS, bool XYZ_SMEM>
 static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
-  auto kern = fps_cull_kernel<P, THREADS>;
-  const size_t smem = (size_t)5 * P * THREADS * sizeof(float);
+  auto kern = fps_cull_kernel<P, THREADS, XYZ_SMEM>;
+  const size_t smem = XYZ_SMEM ? (size_t)P * THREADS * (3 * sizeof(float) + sizeof(uint16_t))
+                               : (size_t)5 * P * THREADS * sizeof(float);
   static bool attr_set = false;   // per instantiation; the attribute is sticky for the process
   if (!attr_set) {
     SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -856,8 +873,8 @@ extern "C" int spc_set_fps_cluster(int cluster_ctas) {
 // streams gains ~5 % overall.  spacap3d_b200/pipeline.py turns it on; SPC_FPS_CULL=0/1 overrides.
 static int g_fps_cull = 0;
 extern "C" int spc_set_fps_cull(int on) {
-  if (on != 0 && on != 1) {
-    set_error("spc_set_fps_cull: %d is not 0 or 1", on);
+  if (on != 0 && on != 1 && on != 2) {
+    set_error("spc_set_fps_cull: %d is not 0, 1 or 2", on);
     return SPC_ERR_INVALID_ARG;
   }
   g_fps_cull = on;
@@ -881,10 +898,11 @@ extern "C" int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, in
   return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, workspace, workspace_bytes, stream_);
 }
 
-static bool fps_cull_enabled() {
-  if (const char *e = getenv("SPC_FPS_CULL")) return atoi(e) != 0;
-  return g_fps_cull != 0;
+static int fps_cull_mode() {
+  if (const char *e = getenv("SPC_FPS_CULL")) return atoi(e);
+  return g_fps_cull;
 }
+static bool fps_cull_enabled() { return fps_cull_mode() != 0; }
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
                     int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_) {
@@ -960,11 +978,12 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
       fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(xyz, N, perm);
       SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
       const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;
+      const bool xyz_smem = fps_cull_mode() == 2;
       switch (P256) {
-        case 8: return launch_fps_cull<8, 256>(p, perm, B, C, stream);
-        case 10: return launch_fps_cull<10, 256>(p, perm, B, C, stream);
-        case 16: return launch_fps_cull<16, 256>(p, perm, B, C, stream);
-        default: return launch_fps_cull<20, 256>(p, perm, B, C, stream);
+        case 8: return xyz_smem ? launch_fps_cull<8, 256, true>(p, perm, B, C, stream) : launch_fps_cull<8, 256, false>(p, perm, B, C, stream);
+        case 10: return xyz_smem ? launch_fps_cull<10, 256, true>(p, perm, B, C, stream) : launch_fps_cull<10, 256, false>(p, perm, B, C, stream);
+        case 16: return xyz_smem ? launch_fps_cull<16, 256, true>(p, perm, B, C, stream) : launch_fps_cull<16, 256, false>(p, perm, B, C, stream);
+        default: return xyz_smem ? launch_fps_cull<20, 256, true>(p, perm, B, C, stream) : launch_fps_cull<20, 256, false>(p, perm, B, C, stream);
       }
     }
   }

@@ -48,23 +48,25 @@ def test_fps_large_clouds(ext, name, monkeypatch):
     workspace, or culling off) and the oracle all agree bit for bit."""
     xyz, m = cases.fps_large_cases()[name]
     want = oracle.furthest_point_sampling(xyz, m)
-    monkeypatch.setenv("SPC_FPS_CULL", "1")
-    got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
-    np.testing.assert_array_equal(got, want)
-    idx2, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m, hint_ordered=True)
-    np.testing.assert_array_equal(idx2.cpu().numpy(), want)
-    np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
+    for mode in ("1", "2"):       # coordinates in registers / in shared memory (three CTAs per SM)
+        monkeypatch.setenv("SPC_FPS_CULL", mode)
+        got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
+        np.testing.assert_array_equal(got, want)
+        idx2, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m, hint_ordered=True)
+        np.testing.assert_array_equal(idx2.cpu().numpy(), want)
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
     monkeypatch.setenv("SPC_FPS_CULL", "0")
     np.testing.assert_array_equal(ext.furthest_point_sampling(cu(xyz), m).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("cluster", [2, 4, 8])
-def test_fps_culled_every_cluster_size(ext, cluster):
+def test_fps_culled_every_cluster_size(ext, cluster, mode):
     from spacap3d_b200 import _lib
     xyz, m = cases.fps_large_cases()["clusters_20000"]
     want = oracle.furthest_point_sampling(xyz, m)
     _lib.call("spc_set_fps_cluster", cluster)
-    _lib.call("spc_set_fps_cull", 1)
+    _lib.call("spc_set_fps_cull", mode)
     try:
         got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
     finally:
@@ -88,13 +90,14 @@ def test_fps_culled_scene_40k(ext):
     from spacap3d_b200 import _lib
     xyz, m = cases.fps_cases()["scene_40k"]
     want = oracle.furthest_point_sampling(xyz, m)
-    _lib.call("spc_set_fps_cull", 1)
-    try:
-        got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
-    finally:
-        _lib.call("spc_set_fps_cull", 0)
-    np.testing.assert_array_equal(got.cpu().numpy(), want)
-    np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
+    for mode in (1, 2):
+        _lib.call("spc_set_fps_cull", mode)
+        try:
+            got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
+        finally:
+            _lib.call("spc_set_fps_cull", 0)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
