@@ -179,6 +179,42 @@ int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz, co
 /* point-major BF16 (B,n,C) -> channel-major f32 (B,C,n) */
 int spc_pm_to_cm(const void *pm_bf16, int B, int n, int C, float *cm, void *stream);
 
+/* ---- training-mode BatchNorm + ReLU of a shared-MLP block -------------------------------------------
+ * Replaces nn.BatchNorm2d(training) + nn.ReLU(inplace=True) of the reference's Conv2d block
+ * (lib/pointnet2/pytorch_utils.py:11-36,39-64,67-120) on y (B,C,S) fp32, S = npoint*nsample:
+ *   forward : batch statistics (biased variance), z = relu((y-mean)*invstd*gamma+beta), running statistics
+ *             updated in place with `momentum` and the unbiased variance (pass NULL to skip), mean / invstd
+ *             saved for backward;
+ *   backward: dy, dgamma, dbeta from dz (gradient w.r.t. z), y and the saved statistics; the ReLU mask is
+ *             recomputed from y.
+ * workspace: spc_bn_relu_workspace_bytes(C) bytes, 8-byte aligned. */
+size_t spc_bn_relu_workspace_bytes(int C);
+int spc_bn_relu_train_forward(const float *y, const float *gamma, const float *beta, int B, int C, int S,
+                              float eps, float momentum, float *running_mean, float *running_var, float *z,
+                              float *save_mean, float *save_invstd, void *workspace, size_t workspace_bytes,
+                              void *stream);
+int spc_bn_relu_train_backward(const float *dz, const float *y, const float *gamma, const float *beta,
+                               const float *save_mean, const float *save_invstd, int B, int C, int S,
+                               float *dy, float *dgamma, float *dbeta, void *workspace, size_t workspace_bytes,
+                               void *stream);
+
+/* Last block of a set-abstraction MLP in training mode: BatchNorm + ReLU + max over the nsample neighbours
+ * (pytorch_utils.py:11-36 followed by F.max_pool2d(kernel=[1,nsample]), pointnet2_modules.py:256-259).
+ * y (B,C,npoint,nsample) -> pooled (B,C,npoint); the normalised activation is never materialised.
+ * argmax (B,C,npoint) uint8 = winning slot (lowest slot on ties, like ATen), ymax = y at that slot; both
+ * are consumed by the backward, which produces dy (B,C,npoint,nsample), dgamma, dbeta from dpool.
+ * nsample must be 16, 32 or 64 (SPC_ERR_UNSUPPORTED otherwise: nothing launched). */
+int spc_bn_relu_maxpool_train_forward(const float *y, const float *gamma, const float *beta, int B, int C,
+                                      int npoint, int nsample, float eps, float momentum,
+                                      float *running_mean, float *running_var, float *pooled,
+                                      uint8_t *argmax, float *ymax, float *save_mean, float *save_invstd,
+                                      void *workspace, size_t workspace_bytes, void *stream);
+int spc_bn_relu_maxpool_train_backward(const float *dpool, const uint8_t *argmax, const float *ymax,
+                                       const float *y, const float *gamma, const float *beta,
+                                       const float *save_mean, const float *save_invstd, int B, int C,
+                                       int npoint, int nsample, float *dy, float *dgamma, float *dbeta,
+                                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,3 +317,88 @@ def pm_to_cm(pm):
     with torch.cuda.device(pm.device):
         _lib.call("spc_pm_to_cm", pm.data_ptr(), B, n, C, cm.data_ptr(), _stream())
     return cm
+
+
+def _bn_workspace(C, device):
+    nbytes = _lib.load().spc_bn_relu_workspace_bytes(int(C))
+    return torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device), nbytes
+
+
+def bn_relu_train_forward(y, gamma, beta, running_mean, running_var, momentum, eps):
+    """Training-mode BatchNorm + ReLU of y (B,C,*) f32 (pytorch_utils.py:11-36,39-64): returns
+    (z, save_mean, save_invstd); running_mean / running_var (or None) are updated in place."""
+    _check(y, "y", torch.float32)
+    _check(gamma, "gamma", torch.float32)
+    _check(beta, "beta", torch.float32)
+    _same_device(y, gamma, beta)
+    B, C = y.shape[0], y.shape[1]
+    S = y.numel() // max(B * C, 1)
+    z = torch.empty_like(y)
+    mean = torch.empty(C, dtype=torch.float32, device=y.device)
+    invstd = torch.empty(C, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        ws, nbytes = _bn_workspace(C, y.device)
+        _lib.call("spc_bn_relu_train_forward", y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, C, S,
+                  float(eps), float(momentum),
+                  running_mean.data_ptr() if running_mean is not None else None,
+                  running_var.data_ptr() if running_var is not None else None,
+                  z.data_ptr(), mean.data_ptr(), invstd.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    return z, mean, invstd
+
+
+def bn_relu_train_backward(dz, y, gamma, beta, mean, invstd):
+    """-> (dy, dgamma, dbeta) for z = relu(batch_norm(y)) given dz."""
+    _check(dz, "dz", torch.float32)
+    _check(y, "y", torch.float32)
+    _same_device(dz, y)
+    B, C = y.shape[0], y.shape[1]
+    S = y.numel() // max(B * C, 1)
+    dy = torch.empty_like(y)
+    dgamma = torch.empty(C, dtype=torch.float32, device=y.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        ws, nbytes = _bn_workspace(C, y.device)
+        _lib.call("spc_bn_relu_train_backward", dz.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                  mean.data_ptr(), invstd.data_ptr(), B, C, S, dy.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                  ws.data_ptr(), nbytes, _stream())
+    return dy, dgamma, dbeta
+
+
+def bn_relu_maxpool_train_forward(y, gamma, beta, running_mean, running_var, momentum, eps):
+    """y (B,C,npoint,nsample) f32 -> (pooled (B,C,npoint), argmax u8, ymax, save_mean, save_invstd):
+    BatchNorm(train) + ReLU + max over nsample without materialising the activation
+    (pytorch_utils.py:11-36 + pointnet2_modules.py:256-259).  Raises SpcUnsupported for nsample not in
+    {16,32,64}."""
+    _check(y, "y", torch.float32)
+    _same_device(y, gamma, beta)
+    B, C, npoint, nsample = y.shape
+    dev = y.device
+    pooled = torch.empty((B, C, npoint), dtype=torch.float32, device=dev)
+    argmax = torch.empty((B, C, npoint), dtype=torch.uint8, device=dev)
+    ymax = torch.empty((B, C, npoint), dtype=torch.float32, device=dev)
+    mean = torch.empty(C, dtype=torch.float32, device=dev)
+    invstd = torch.empty(C, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws, nbytes = _bn_workspace(C, dev)
+        _lib.call("spc_bn_relu_maxpool_train_forward", y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, C,
+                  npoint, nsample, float(eps), float(momentum),
+                  running_mean.data_ptr() if running_mean is not None else None,
+                  running_var.data_ptr() if running_var is not None else None,
+                  pooled.data_ptr(), argmax.data_ptr(), ymax.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                  ws.data_ptr(), nbytes, _stream())
+    return pooled, argmax, ymax, mean, invstd
+
+
+def bn_relu_maxpool_train_backward(dpool, argmax, ymax, y, gamma, beta, mean, invstd):
+    """-> (dy (B,C,npoint,nsample), dgamma, dbeta)."""
+    _check(dpool, "dpool", torch.float32)
+    _same_device(dpool, y)
+    B, C, npoint, nsample = y.shape
+    dy = torch.empty_like(y)
+    dgamma = torch.empty(C, dtype=torch.float32, device=y.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=y.device)
+    with torch.cuda.device(y.device):
+        _lib.call("spc_bn_relu_maxpool_train_backward", dpool.data_ptr(), argmax.data_ptr(), ymax.data_ptr(),
+                  y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), B, C,
+                  npoint, nsample, dy.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    return dy, dgamma, dbeta

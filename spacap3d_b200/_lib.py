@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -27,6 +27,11 @@ SIGNATURES = {
     "spc_ball_query_ex": [_p, _p, _i, _i, _i, _f, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_group_points": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "spc_bn_relu_train_forward": [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p],
+    "spc_bn_relu_maxpool_train_forward": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
+                                          ctypes.c_size_t, _p],
+    "spc_bn_relu_maxpool_train_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p],
+    "spc_bn_relu_train_backward": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, ctypes.c_size_t, _p],
     "spc_group_points_grad_ex": [_p, _p, _i, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_three_nn": [_p, _p, _i, _i, _i, _p, _p, _p],
     "spc_three_interpolate": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
@@ -65,6 +70,8 @@ def load():
     lib.spc_ball_query_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_group_points_grad_workspace_bytes.argtypes = [_i, _i, _i, _i]
     lib.spc_group_points_grad_workspace_bytes.restype = ctypes.c_size_t
+    lib.spc_bn_relu_workspace_bytes.argtypes = [_i]
+    lib.spc_bn_relu_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_fps_workspace_bytes.argtypes = [_i, _i, _i]
     lib.spc_fps_workspace_bytes.restype = ctypes.c_size_t
     for name, argtypes in SIGNATURES.items():

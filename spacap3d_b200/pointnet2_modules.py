@@ -244,6 +244,10 @@ class PointnetSAModuleVotes(nn.Module):
         if fused is not None:
             return new_xyz, fused, inds
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        if (self.pooling == 'max' and self.training and grouped_features.is_cuda and len(self.mlp_module) > 0
+                and pt_utils.FUSED_BN_RELU_TRAINING):
+            # training: the last block's BatchNorm + ReLU + max-pool run as one kernel pair (csrc/bn_relu.cu)
+            return new_xyz, self.mlp_module.forward_max_pooled(grouped_features), inds
         new_features = self.mlp_module(grouped_features)      # (B, mlp[-1], npoint, nsample)
         if self.pooling == 'max':
             new_features = F.max_pool2d(new_features, kernel_size=[1, new_features.size(3)])

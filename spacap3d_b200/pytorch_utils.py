@@ -6,7 +6,57 @@ The state-dict contract (SURVEY F11) is what matters: a SharedMLP owns `layer{i}
 a sequential block with `conv` (bias only when there is no BN), `bn` (itself a block with one
 child `bn`) and `activation`, so keys read `...layer0.conv.weight`, `...layer0.bn.bn.running_mean`.
 """
+import torch
 import torch.nn as nn
+
+# Training mode: run BatchNorm2d + ReLU of a conv block through the fused sm_100a kernels (csrc/bn_relu.cu)
+# instead of cuDNN batch-norm + a separate ReLU pass.  Same parameters, buffers and results (fp32, within
+# summation-order rounding); set to False to get the plain module sequence.
+FUSED_BN_RELU_TRAINING = True
+
+
+class _BnReluTrain(torch.autograd.Function):
+    """z = relu(batch_norm(y, training=True)); saves y and the batch statistics, recomputes the ReLU mask."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps):
+        from . import _ext
+        z, mean, invstd = _ext.bn_relu_train_forward(y, gamma, beta, running_mean, running_var, momentum, eps)
+        ctx.save_for_backward(y, gamma, beta, mean, invstd)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from . import _ext
+        y, gamma, beta, mean, invstd = ctx.saved_tensors
+        dy, dgamma, dbeta = _ext.bn_relu_train_backward(dz.contiguous(), y, gamma, beta, mean, invstd)
+        return dy, dgamma, dbeta, None, None, None, None
+
+
+def _max_pool_last(x):
+    """The SA module's pooling (pointnet2_modules.py:256-259) for the shapes the fused kernel does not take."""
+    return torch.nn.functional.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
+class _BnReluMaxPoolTrain(torch.autograd.Function):
+    """pooled = max_k relu(batch_norm(y, training=True))[..., k] for y (B,C,npoint,nsample)."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, running_mean, running_var, momentum, eps):
+        from . import _ext
+        pooled, argmax, ymax, mean, invstd = _ext.bn_relu_maxpool_train_forward(
+            y, gamma, beta, running_mean, running_var, momentum, eps)
+        ctx.save_for_backward(y, gamma, beta, mean, invstd, argmax, ymax)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpool):
+        from . import _ext
+        y, gamma, beta, mean, invstd, argmax, ymax = ctx.saved_tensors
+        dy, dgamma, dbeta = _ext.bn_relu_maxpool_train_backward(dpool.contiguous(), argmax, ymax, y, gamma, beta,
+                                                                mean, invstd)
+        return dy, dgamma, dbeta, None, None, None, None
+
 
 _CONV = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}
 _NORM = {1: nn.BatchNorm1d, 2: nn.BatchNorm2d, 3: nn.BatchNorm3d}
@@ -61,6 +111,39 @@ class _ConvBase(nn.Sequential):
         self.add_module(name + "conv", conv_unit)
         if not preact:
             _norm_act()
+        # conv -> BatchNorm2d -> ReLU is the only arrangement SpaCap3D instantiates; remember it for forward()
+        self._fusable = (not preact and norm_unit is not None and isinstance(activation, nn.ReLU)
+                         and isinstance(conv_unit, nn.Conv2d))
+        self._conv_name, self._bn_name = name + "conv", name + "bn"   # names, not modules: no second registration
+
+    def _fused_training_ok(self, x):
+        if not (self._fusable and FUSED_BN_RELU_TRAINING and self.training and x.is_cuda
+                and x.dtype == torch.float32 and torch.is_grad_enabled()):
+            return False
+        bn = getattr(self, self._bn_name)[0]
+        return bn.training and bn.affine and bn.track_running_stats and bn.momentum is not None
+
+    def forward(self, x, max_pool_last_dim=False):
+        """max_pool_last_dim=True additionally takes the max over the last axis (the SA module's
+        F.max_pool2d(kernel=[1, nsample]) + squeeze) and returns (B, C, npoint)."""
+        if self._fused_training_ok(x):
+            bn = getattr(self, self._bn_name)[0]
+            y = getattr(self, self._conv_name)(x)
+            if y.is_contiguous() and y.shape[0] * y.shape[1] <= 65535:
+                args = (y, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps))
+                if max_pool_last_dim and y.dim() == 4 and y.shape[3] in (16, 32, 64):
+                    out = _BnReluMaxPoolTrain.apply(*args)
+                else:
+                    out = _BnReluTrain.apply(*args)
+                    if max_pool_last_dim:
+                        out = _max_pool_last(out)
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                return out
+            out = torch.relu_(getattr(self, self._bn_name)(y))
+        else:
+            out = super().forward(x)
+        return _max_pool_last(out) if max_pool_last_dim else out
 
 
 def _make_conv(dim, wrapper):
@@ -96,6 +179,14 @@ class SharedMLP(nn.Sequential):
             self.add_module(name + "layer{}".format(i),
                             Conv2d(cin, cout, bn=bn and not plain,
                                    activation=None if plain else activation, preact=preact))
+
+    def forward_max_pooled(self, x):
+        """self(x) followed by the max over the last axis, with the last block's BatchNorm + ReLU + max
+        fused in training mode (csrc/bn_relu.cu); returns (B, C_out, npoint)."""
+        blocks = list(self.children())
+        for blk in blocks[:-1]:
+            x = blk(x)
+        return blocks[-1](x, max_pool_last_dim=True)
 
 
 class FC(nn.Sequential):
