@@ -109,10 +109,16 @@ def main():
         if ref is not None:
             import bench
 
-            def theirs():
+            from spacap3d_b200 import pytorch_utils
+
+            def theirs():      # reference extension + the plain cuDNN BatchNorm / ReLU / max_pool2d sequence
                 model.zero_grad(set_to_none=True)
-                with bench.swapped_ops(ref, host_decode=False):
-                    step(model, pc, 1)
+                pytorch_utils.FUSED_BN_RELU_TRAINING = False
+                try:
+                    with bench.swapped_ops(ref, host_decode=False):
+                        step(model, pc, 1)
+                finally:
+                    pytorch_utils.FUSED_BN_RELU_TRAINING = True
 
             try:
                 rms = time_steps(theirs, max(2, args.iters // 2), warmup=1)
