@@ -37,9 +37,10 @@ def allreduce_gradients(module, average=True):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     if average:
         flat /= dist.get_world_size()
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)        # one multi-tensor kernel instead of ~100 small copies
     return flat.numel()
