@@ -298,6 +298,7 @@ def run_ours(args):
         # the knobs are baked into the captured graphs; eager passes stay on the single-call defaults
         _lib.call("spc_set_fps_cluster", 0)
         _lib.call("spc_set_fps_cull", 0)
+        _lib.call("spc_set_sa_min_tiles", 0)
 
         def timed_graph(submit, steps, warmup, sampler=None):
             for i in range(warmup):

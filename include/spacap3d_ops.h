@@ -130,6 +130,12 @@ int spc_three_interpolate(const float *points, const int32_t *idx, const float *
 int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const float *weight,
                                int B, int C, int n, int m, float *grad_points, void *stream);
 
+/* Tuning knob, process-wide (0 = one CTA per SM, the latency optimum): give every CTA of the fused
+ * set-abstraction kernel at least this many 128-row tiles, i.e. launch fewer CTAs for the small layers.
+ * Results do not change.  With several batches in flight the freed SMs run other streams' kernels:
+ * +4.5 % scenes/s at 16 on B200 (12 streams), -6 % for a single stream. */
+int spc_set_sa_min_tiles(int tiles_per_cta);
+
 /* Fused set-abstraction forward, eval mode (no reference C++ counterpart: it replaces the whole
  * Python/ATen/cuDNN sequence of PointnetSAModuleVotes.forward after the ball query --
  * pointnet2_utils.py:351-362 (2x group_points, sub, div, cat), pytorch_utils.py:11-36 (SharedMLP =

@@ -616,6 +616,8 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
   }
 }
 
+static int g_sa_min_tiles = 0;
+
 template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
 static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   using L = SaPipeSmem<C1, C2, C3>;
@@ -624,6 +626,12 @@ static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = kNumSMs;
   if (grid > p.num_tiles) grid = p.num_tiles;
+  // Throughput knob: every CTA pays a fixed cost (weight staging, TMEM allocation, pipeline fill); with few
+  // tiles per CTA that cost dominates and a smaller grid spends less SM-time for the same work (slower alone,
+  // faster when other streams can use the freed SMs).
+  int min_tiles = g_sa_min_tiles;
+  if (const char *e = getenv("SPC_SA_MIN_TILES")) min_tiles = atoi(e);
+  if (min_tiles > 0) grid = max(1, min(grid, (p.num_tiles + min_tiles - 1) / min_tiles));
   kern<<<grid, SAP_THREADS, smem, stream>>>(p);
   SPC_LAUNCH_CHECK("sa_fused_pipe_kernel");
   return SPC_OK;
@@ -632,6 +640,15 @@ static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
 }  // namespace spc
 
 using namespace spc;
+
+extern "C" int spc_set_sa_min_tiles(int tiles_per_cta) {
+  if (tiles_per_cta < 0 || tiles_per_cta > 4096) {
+    set_error("spc_set_sa_min_tiles: %d out of range", tiles_per_cta);
+    return SPC_ERR_INVALID_ARG;
+  }
+  g_sa_min_tiles = tiles_per_cta;
+  return SPC_OK;
+}
 
 extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *idx,
                                     const void *G_bf16, const float *feat, const float *W0,

@@ -20,7 +20,7 @@ class GraphedDetector:
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
     def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None,
-                 fps_cull=2):
+                 fps_cull=2, sa_min_tiles=16):
         assert example.is_cuda
         # FPS cluster size: automatic (8 CTAs of 256 threads, two CTAs per SM) unless overridden
         if fps_cluster is None:
@@ -32,6 +32,8 @@ class GraphedDetector:
         # per SM) takes 1.63 ms per call instead of 1.24 but a scene holds 2.7 SMs instead of 4:
         # +10 % scenes/s over mode 1 and +14 % over the plain kernel at 12 streams (B200, 8 x 40k).
         _lib.call("spc_set_fps_cull", int(fps_cull))
+        # same reasoning for the fused SA kernel: fewer, longer-lived CTAs for the small layers
+        _lib.call("spc_set_sa_min_tiles", int(sa_min_tiles))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)

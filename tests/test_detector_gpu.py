@@ -160,3 +160,4 @@ def test_graphed_pipeline_equals_eager():
     finally:
         _lib.call("spc_set_fps_cull", 0)
         _lib.call("spc_set_fps_cluster", 0)
+        _lib.call("spc_set_sa_min_tiles", 0)
