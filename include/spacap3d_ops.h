@@ -67,6 +67,18 @@ int spc_set_fps_cull(int on);
 int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                    float *new_xyz, int hint_ordered, void *workspace,
                                    size_t workspace_bytes, void *stream);
+/* Same, with the "strict sequence" side channel that lets a chain of samplers (SA1 -> SA2 -> SA3 -> SA4 each
+ * sample from the previous output, models/backbone_module.py:107-127) skip even the proof kernels:
+ *   strict_out    (B) int32 device, nullable: 1 = every pick of THIS call was the strict unique maximum of the
+ *                 min-distances (tracked exactly by the culled kernels, implied by a successful proof), so FPS over
+ *                 any prefix of the output is provably the identity; 0 = a tie occurred or it was not tracked.
+ *   known_ordered (B) int32 device, nullable: strict_out of the call that produced `xyz` (npoint <= N);
+ *                 scenes flagged 1 skip the proof and the sequential rounds, the others behave as with
+ *                 hint_ordered alone. */
+int spc_furthest_point_sampling_ex2(const float *xyz, int B, int N, int npoint, int32_t *idx,
+                                    float *new_xyz, int hint_ordered, const int32_t *known_ordered,
+                                    int32_t *strict_out, void *workspace, size_t workspace_bytes,
+                                    void *stream);
 
 /* gather_points(points, idx)                             sampling.cpp:15-38, sampling_gpu.cu:8-30
  * points (B,C,N), idx (B,M) -> out (B,C,M) */

@@ -60,19 +60,36 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
-def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False):
+def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False, known_ordered=None, want_strict=False):
     """Extension: FPS that also returns the sampled coordinates (B,nsamples,3) from the same
     kernel (the gather that always follows FPS, pointnet2_modules.py:237-242).
 
     hint_ordered=True tells the library that `points` is probably itself an FPS output (SA2..SA4
     sample from the previous layer's centres); it then PROVES, with two parallel kernels, whether
     the result is 0..nsamples-1 and skips the sequential rounds for the scenes where it is.  The
-    returned indices are identical with or without the hint (spc_furthest_point_sampling_ex)."""
+    returned indices are identical with or without the hint (spc_furthest_point_sampling_ex).
+
+    want_strict=True additionally returns a (B,) int32 device tensor: 1 = every pick was the strict unique
+    maximum, i.e. the OUTPUT is a strict FPS sequence; passing it as `known_ordered` to the call that samples
+    from that output skips proof and rounds for the flagged scenes (spc_furthest_point_sampling_ex2)."""
     _check(points, "points", torch.float32)
     _same_device(points)
     B, N, _ = points.shape
     out = torch.empty((B, nsamples), dtype=torch.int32, device=points.device)
     new_xyz = torch.empty((B, nsamples, 3), dtype=torch.float32, device=points.device)
+    if want_strict or known_ordered is not None:
+        strict = torch.empty(B, dtype=torch.int32, device=points.device) if want_strict else None
+        if known_ordered is not None:
+            _check(known_ordered, "known_ordered", torch.int32)
+            assert known_ordered.numel() == B and nsamples <= N
+        with torch.cuda.device(points.device):
+            nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
+            _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
+                      new_xyz.data_ptr(), int(bool(hint_ordered) and 2 <= nsamples <= N),
+                      known_ordered.data_ptr() if known_ordered is not None else None,
+                      strict.data_ptr() if strict is not None else None, ws.data_ptr(), nbytes, _stream())
+        return (out, new_xyz, strict) if want_strict else (out, new_xyz)
     with torch.cuda.device(points.device):
         if (hint_ordered and 2 <= nsamples <= N) or (N >= FPS_WORKSPACE_MIN_N and nsamples >= 2):
             nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -19,6 +19,7 @@ _f = ctypes.c_float
 SIGNATURES = {
     "spc_furthest_point_sampling": [_p, _i, _i, _i, _p, _p, _p],
     "spc_furthest_point_sampling_ex": [_p, _i, _i, _i, _p, _p, _i, _p, ctypes.c_size_t, _p],
+    "spc_furthest_point_sampling_ex2": [_p, _i, _i, _i, _p, _p, _i, _p, _p, _p, ctypes.c_size_t, _p],
     "spc_set_fps_cluster": [_i],
     "spc_set_fps_cull": [_i],
     "spc_set_sa_min_tiles": [_i],

@@ -39,6 +39,7 @@ struct FpsParams {
   int N, npoint;
   int T, log2T, Q;    // reference thread count, its log2, ceil(N/T)
   const int *ordered_ok;  // per scene: 1 = "FPS(xyz)[0:npoint] is provably 0..npoint-1" (or nullptr)
+  int *strict_out;        // per scene (or nullptr): 1 = every pick was the strict unique maximum (culled kernels)
 };
 
 __device__ __forceinline__ int fps_v_to_k(unsigned v, int Q, int T, int log2T) {
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
   // npoint sequential rounds would return 0..npoint-1.  Every CTA of the cluster reads the same
   // flag, so they all leave together.
   if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {
+    if (g == 0 && p.strict_out) p.strict_out[scene] = 1;   // proven: every pick was a strict unique maximum
     int32_t *oidx = p.idx + (size_t)scene * p.npoint;
     for (unsigned j = g; j < (unsigned)p.npoint; j += C * THREADS) oidx[j] = (int)j;
     if (p.new_xyz) {
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
       if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
     }
   }
+  if (writer && p.strict_out) p.strict_out[scene] = 0;   // this kernel does not track ties: "unknown"
   if (C > 1) cluster.sync();  // no CTA may exit while a peer can still store into its smem
 }
 
@@ -428,7 +431,8 @@ __device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned 
 //   the (few) warps that are not culled, point indices are kept as uint16 and the tie-break index is
 //   recomputed from them => <= 80 regs and 70 KB smem: THREE CTAs per SM, i.e. a scene occupies 2.7 SMs
 //   instead of 4 for the duration of the call.
-template <int P, int THREADS, bool XYZ_SMEM>
+// TRACK = true additionally maintains p.strict_out (see below); compiled out otherwise (it costs registers).
+template <int P, int THREADS, bool XYZ_SMEM, bool TRACK>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (XYZ_SMEM ? 3 : 2) : 1))
 fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
   constexpr int NW = THREADS / 32;
@@ -457,6 +461,7 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
   const unsigned g = rank * THREADS + tid;
   const unsigned q0 = g * P;                    // first Morton-sorted position owned by this thread
   if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {   // verified shortcut, as in fps_cluster_kernel
+    if (g == 0 && p.strict_out) p.strict_out[scene] = 1;       // the proof implies strict unique maxima
     int32_t *oidx = p.idx + (size_t)scene * p.npoint;
     for (unsigned j = g; j < (unsigned)p.npoint; j += C * THREADS) oidx[j] = (int)j;
     if (p.new_xyz) {
@@ -528,6 +533,7 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
   if (writer) {
     idx[0] = 0;
     if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
+    if (TRACK && p.strict_out) p.strict_out[scene] = 1;   // cleared by whoever sees a tie (ordered by the sync below)
   }
   const unsigned tx_bytes = 24u * C;
   uint32_t r_slot0 = 0, r_slot1 = 0, r_bar0 = 0, r_bar1 = 0;
@@ -559,14 +565,25 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
 
   // arg-max over the lanes holding (key, v): largest key, then smallest v.  The common case (a unique
   // maximum) costs two dependent redux; the ballot that detects ties issues alongside the second.
-  auto argmax_lane = [&](bool valid, unsigned key, unsigned v, unsigned &kmax) -> unsigned {
+  auto argmax_lane = [&](bool valid, unsigned key, unsigned v, unsigned &kmax, bool &tied) -> unsigned {
     kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
     const bool hit = valid && key == kmax;
     unsigned src = __reduce_min_sync(0xffffffffu, hit ? lane : 32u);
     const unsigned ties = __ballot_sync(0xffffffffu, hit);
-    if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fps_resolve_tie(hit, v, lane);   // rare
+    tied = kmax != 0u && (ties & (ties - 1u)) != 0u;
+    if (tied) src = fps_resolve_tie(hit, v, lane);   // rare
     return src & 31u;
   };
+  // "Every pick so far was the strict unique maximum" (p.strict_out): then FPS over any prefix of the OUTPUT is
+  // the identity, which lets the next set-abstraction layers skip their sampling without the proof kernels.
+  // Kept off the round's dependency chain: ties between warps / CTAs are seen by every thread (`strict`), ties
+  // inside the winning warp or thread are checked lazily by the ONE thread that owns the round's winner, which
+  // then stores 0 (the flag was initialised to 1 before the first round).
+  bool strict = true;        // uniform: no tie at CTA / cluster level so far, and every round had a candidate
+  bool own_r = false;        // this lane published the warp's current candidate ...
+  bool wt_r = false;         // ... which tied with another lane of the warp
+  float best_r = -1.0f;      // this thread's best min-distance at its last update
+  int mk_r = -1;             // and the point that holds it
 
   for (int j = 1; j < p.npoint; ++j) {
     const int buf = j & 1;
@@ -606,13 +623,15 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
       const int mk = XYZ_SMEM ? (int)sk16[bs * THREADS + tid] : sk[bs * THREADS + tid];
       const unsigned mv = XYZ_SMEM ? v_of_k((unsigned)mk) : sv[bs * THREADS + tid];
       const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-      const unsigned wsrc = argmax_lane(true, key, mv, ck);
+      bool wtied;
+      const unsigned wsrc = argmax_lane(true, key, mv, ck, wtied);
       if (lane == wsrc) {
         FpsCandV *e = &w_cand[buf][warp];
         *reinterpret_cast<uint4 *>(e) = make_uint4(ck, mv, (unsigned)mk, __float_as_uint(mx));
         *reinterpret_cast<float2 *>(&e->y) = make_float2(my, mz);
       }
       my_k = ck ? __shfl_sync(0xffffffffu, mk, wsrc) : -1;   // consumed next round only
+      if (TRACK) { own_r = lane == wsrc; wt_r = wtied; best_r = best; mk_r = mk; }
       fresh = true;
       stale = true;
     } else if (stale) {
@@ -633,9 +652,11 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
       eyz = *reinterpret_cast<const float2 *>(&w_cand[buf][lane].y);
     }
     unsigned bmax;
-    unsigned src = argmax_lane(lane < NW, e4.x, e4.y, bmax);
+    bool ctied;
+    unsigned src = argmax_lane(lane < NW, e4.x, e4.y, bmax, ctied);
     unsigned bv = __shfl_sync(0xffffffffu, e4.y, src);
     unsigned wk = __shfl_sync(0xffffffffu, e4.z, src);
+    if (TRACK) strict = strict && !ctied;
     unsigned wxb = __shfl_sync(0xffffffffu, e4.w, src);
     float wy = __shfl_sync(0xffffffffu, eyz.x, src);
     float wz = __shfl_sync(0xffffffffu, eyz.y, src);
@@ -653,26 +674,35 @@ fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
         e4 = *reinterpret_cast<const uint4 *>(&c_cand[buf][lane]);
         eyz = *reinterpret_cast<const float2 *>(&c_cand[buf][lane].y);
       }
-      src = argmax_lane(lane < C, e4.x, e4.y, bmax);
+      src = argmax_lane(lane < C, e4.x, e4.y, bmax, ctied);
       wk = __shfl_sync(0xffffffffu, e4.z, src);
+      if (TRACK) strict = strict && !ctied;
       wxb = __shfl_sync(0xffffffffu, e4.w, src);
       wy = __shfl_sync(0xffffffffu, eyz.x, src);
       wz = __shfl_sync(0xffffffffu, eyz.y, src);
     }
     old = 0;
+    if (TRACK) strict = strict && bmax != 0u;
     if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
     else { ox = __uint_as_float(wxb); oy = wy; oz = wz; old = (int)wk; }
+    if (TRACK && own_r && bmax != 0u && old == mk_r) {   // one thread of the cluster per round
+      int eq = 0;
+#pragma unroll
+      for (int s = 0; s < P; ++s) eq += (t[s] == best_r) ? 1 : 0;
+      if (wt_r || eq > 1) p.strict_out[scene] = 0;
+    }
     if (writer) {
       idx[j] = old;
       if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
     }
   }
+  if (writer && p.strict_out && (!TRACK || !strict)) p.strict_out[scene] = 0;
   if (C > 1) cluster.sync();
 }
 
-template <int P, int THREADS, bool XYZ_SMEM>
-static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
-  auto kern = fps_cull_kernel<P, THREADS, XYZ_SMEM>;
+template <int P, int THREADS, bool XYZ_SMEM, bool TRACK>
+static int launch_fps_cull_t(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
+  auto kern = fps_cull_kernel<P, THREADS, XYZ_SMEM, TRACK>;
   const size_t smem = XYZ_SMEM ? (size_t)P * THREADS * (3 * sizeof(float) + sizeof(uint16_t))
                                : (size_t)5 * P * THREADS * sizeof(float);
   static bool attr_set = false;   // per instantiation; the attribute is sticky for the process
@@ -694,6 +724,12 @@ static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C
   cfg.numAttrs = 1;
   SPC_CUDA(cudaLaunchKernelEx(&cfg, kern, p, perm));
   return SPC_OK;
+}
+
+template <int P, int THREADS, bool XYZ_SMEM>
+static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
+  return p.strict_out ? launch_fps_cull_t<P, THREADS, XYZ_SMEM, true>(p, perm, B, C, stream)
+                      : launch_fps_cull_t<P, THREADS, XYZ_SMEM, false>(p, perm, B, C, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -727,9 +763,11 @@ __device__ __forceinline__ bool fps_skipped(float x, float y, float z) {
 // p_0 is one the reference never selects (|p|^2 <= 1e-3)
 __global__ void __launch_bounds__(CHK_THREADS) fps_prefix_dist_kernel(const float *__restrict__ xyz, int N,
                                                                        int npoint, float *__restrict__ D,
-                                                                       int *__restrict__ ok) {
+                                                                       int *__restrict__ ok,
+                                                                       const int *__restrict__ known) {
   __shared__ float sx[CHK_TILE], sy[CHK_TILE], sz[CHK_TILE];
   const int b = blockIdx.y;
+  if (known != nullptr && known[b] != 0) return;   // already established by the call that produced xyz
   const float *P = xyz + (size_t)b * N * 3;
   const int j = blockIdx.x * CHK_THREADS + threadIdx.x;
   const bool act = j < npoint;
@@ -766,9 +804,11 @@ __global__ void __launch_bounds__(CHK_THREADS) fps_prefix_dist_kernel(const floa
 __global__ void __launch_bounds__(CHK_THREADS) fps_prefix_check_kernel(const float *__restrict__ xyz, int N,
                                                                         int npoint,
                                                                         const float *__restrict__ D,
-                                                                        int *__restrict__ ok) {
+                                                                        int *__restrict__ ok,
+                                                                        const int *__restrict__ known) {
   __shared__ float sx[CHK_TILE], sy[CHK_TILE], sz[CHK_TILE], sd[CHK_TILE];
   const int b = blockIdx.y;
+  if (known != nullptr && known[b] != 0) return;
   const float *P = xyz + (size_t)b * N * 3;
   const float *Db = D + (size_t)b * npoint;
   const int k = blockIdx.x * CHK_THREADS + threadIdx.x;
@@ -850,7 +890,8 @@ using namespace spc;
   case PV: return launch_fps<PV, TH, REGS>(p, B, C, stream);
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
-                    int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_);
+                    int hint_ordered, const int32_t *known_ordered, int32_t *strict_out, void *workspace,
+                    size_t workspace_bytes, void *stream_);
 
 // process-wide tuning knob (0 = automatic).  8-CTA clusters minimise the latency of one call;
 // 4-CTA clusters cost ~15 % more time per call but half the SM-time, which is what matters when
@@ -888,14 +929,22 @@ extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
 
 extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint,
                                            int32_t *idx, float *new_xyz, void *stream_) {
-  return fps_impl(xyz, B, N, npoint, idx, new_xyz, 0, nullptr, 0, stream_);
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, 0, nullptr, nullptr, nullptr, 0, stream_);
 }
 
 extern "C" int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint,
                                               int32_t *idx, float *new_xyz, int hint_ordered,
                                               void *workspace, size_t workspace_bytes,
                                               void *stream_) {
-  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, workspace, workspace_bytes, stream_);
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, nullptr, nullptr, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int spc_furthest_point_sampling_ex2(const float *xyz, int B, int N, int npoint, int32_t *idx,
+                                               float *new_xyz, int hint_ordered, const int32_t *known_ordered,
+                                               int32_t *strict_out, void *workspace, size_t workspace_bytes,
+                                               void *stream_) {
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, known_ordered, strict_out, workspace,
+                  workspace_bytes, stream_);
 }
 
 static int fps_cull_mode() {
@@ -905,7 +954,8 @@ static int fps_cull_mode() {
 static bool fps_cull_enabled() { return fps_cull_mode() != 0; }
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
-                    int hint_ordered, void *workspace, size_t workspace_bytes, void *stream_) {
+                    int hint_ordered, const int32_t *known_ordered, int32_t *strict_out, void *workspace,
+                    size_t workspace_bytes, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   SPC_CHECK_ARG(xyz && (idx || npoint == 0 || B == 0), "fps: null pointer");
   if (B == 0 || npoint == 0) return SPC_OK;
@@ -917,6 +967,7 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   while ((1 << p.log2T) < p.T) ++p.log2T;
   p.Q = (N + p.T - 1) / p.T;
   p.ordered_ok = nullptr;
+  p.strict_out = strict_out;
   // ---- optional verified shortcut for FPS-ordered inputs ---------------------------------------
   if (hint_ordered && workspace && npoint >= 2 && npoint <= N &&
       workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && B <= 65535 &&
@@ -924,11 +975,12 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
     float *D = reinterpret_cast<float *>(workspace);
     int *ok = reinterpret_cast<int *>(D + (size_t)B * npoint);
     fps_fill_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(ok, B, 1);
-    fps_prefix_dist_kernel<<<dim3(ceil_div(npoint, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok);
-    fps_prefix_check_kernel<<<dim3(ceil_div(N, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok);
+    fps_prefix_dist_kernel<<<dim3(ceil_div(npoint, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok, known_ordered);
+    fps_prefix_check_kernel<<<dim3(ceil_div(N, CHK_THREADS), B), CHK_THREADS, 0, stream>>>(xyz, N, npoint, D, ok, known_ordered);
     SPC_LAUNCH_CHECK("fps_prefix_check");
     p.ordered_ok = ok;
   }
+  if (p.ordered_ok == nullptr && known_ordered != nullptr && npoint <= N) p.ordered_ok = known_ordered;
   const long long V = (long long)p.T * p.Q;
 
   // ---- small clouds: one CTA of 256 threads -------------------------------------------------

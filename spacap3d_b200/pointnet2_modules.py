@@ -24,6 +24,13 @@ from . import _lib
 FAST_PATHS = True
 
 
+import os as _os
+# Chain the samplers through spc_furthest_point_sampling_ex2's "strict sequence" flags (SA2-SA4 then skip the
+# proof kernels as well).  Exact and tested, but measured neutral on B200 (the tie tracking slows the culled SA1
+# kernel by 2 %, which cancels the ~3 % saved on the proof kernels: 11.7-11.9 k scenes/s either way), so off.
+FPS_STRICT_FLAGS = _os.environ.get("SPC_FPS_STRICT", "0") == "1"
+
+
 def _sample_centres(xyz, npoint, inds=None):
     """FPS (unless indices are supplied) + gather of the sampled coordinates.
     Returns (new_xyz (B,npoint,3) or None, inds)."""
@@ -34,9 +41,18 @@ def _sample_centres(xyz, npoint, inds=None):
         # one kernel: the FPS epilogue already holds the winners' coordinates.  Centres produced by
         # an FPS are tagged so that the next layer can try the verified "already FPS-ordered"
         # shortcut (exact: see spc_furthest_point_sampling_ex).
+        # `_spc_fps_strict` carries the producing call's per-scene "strict sequence" flags: flagged scenes
+        # need neither the proof nor the rounds.
         hint = bool(getattr(xyz, "_spc_fps_ordered", False))
-        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
+        if not FPS_STRICT_FLAGS:
+            inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
+            new_xyz._spc_fps_ordered = True
+            return new_xyz, inds
+        known = getattr(xyz, "_spc_fps_strict", None) if hint and npoint <= xyz.shape[1] else None
+        inds, new_xyz, strict = _ext.furthest_point_sampling_with_xyz(
+            xyz.contiguous(), npoint, hint_ordered=hint, known_ordered=known, want_strict=True)
         new_xyz._spc_fps_ordered = True
+        new_xyz._spc_fps_strict = strict
         return new_xyz, inds
     if inds is None:
         inds = pointnet2_utils.furthest_point_sample(xyz, npoint)

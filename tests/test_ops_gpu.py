@@ -75,6 +75,41 @@ def test_fps_culled_every_cluster_size(ext, cluster, mode):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fps_strict_sequence_flags_and_chain(ext, mode):
+    """spc_furthest_point_sampling_ex2: the culled kernels report per scene whether every pick was a strict
+    unique maximum; the next samplers use that instead of the proof kernels.  Whatever the flags say, every
+    level of the 40k -> 2048 -> 1024 -> 512 -> 256 chain equals the oracle; a clean scene must be flagged 1 by
+    the culled kernels (so the shortcut is really exercised), scenes with exact ties 0."""
+    from spacap3d_b200 import _lib
+    sc, _ = cases.fps_cases()["scene_40k"]                        # scene 1 has duplicated points
+    lat = cases.fps_large_cases()["lattice_13824"][0][:1]          # exact ties everywhere
+    _lib.call("spc_set_fps_cull", mode)
+    try:
+        for xyz, expect in ((sc, [1, 0]), (lat, [0])):
+            cur_np, cur = xyz, cu(xyz)
+            known, hint = None, False
+            for lvl, m in enumerate((2048, 1024, 512, 256)):
+                if m > cur_np.shape[1]:
+                    break
+                idx, new_xyz, strict = ext.furthest_point_sampling_with_xyz(cur, m, hint_ordered=hint,
+                                                                             known_ordered=known, want_strict=True)
+                want = oracle.furthest_point_sampling(cur_np, m)
+                np.testing.assert_array_equal(idx.cpu().numpy(), want)
+                cur_np = cases.fps_follow_on(cur_np, want, m)
+                np.testing.assert_array_equal(new_xyz.cpu().numpy(), cur_np)
+                flags = strict.cpu().numpy().tolist()
+                if lvl == 0:
+                    assert flags == (expect if mode else [0] * len(expect)), (mode, flags)
+                for b, f in enumerate(flags):                     # a flag of 1 is a promise: identity below
+                    if f and m // 2 >= 1:
+                        sub_idx = oracle.furthest_point_sampling(cur_np[b:b + 1], m // 2)
+                        np.testing.assert_array_equal(sub_idx[0], np.arange(m // 2))
+                cur, known, hint = new_xyz, strict, True
+    finally:
+        _lib.call("spc_set_fps_cull", 0)
+
+
 def test_fps_config5_200k_points(ext):
     """BASELINE config 5's largest cloud: 200 000 points -> 8192 samples (a 16-CTA cluster), one scene."""
     from spacap3d_b200.scenes import make_scene_xyz
