@@ -233,6 +233,20 @@ int spc_bn_relu_maxpool_train_backward(const float *dpool, const uint8_t *argmax
                                        int npoint, int nsample, float *dy, float *dgamma, float *dbeta,
                                        void *stream);
 
+/* ---- detection post-processing: device side of parse_predictions, lib/ap_helper.py:44-160 ----
+ * spc_box_point_counts: counts[b,k] = number of points of scene b inside predicted box k (the reference's
+ *   extract_pc_in_box3d / scipy Delaunay hull test per box, ap_helper.py:69-79, data/scannet/model_util_scannet.py:
+ *   13-22).  points (B,N,point_stride) f32 (xyz first), corners (B,K,8,3) f64 in get_3d_box_batch order
+ *   (utils/box_util.py:360-383; rotated boxes are handled).
+ * spc_nms_boxes: pick[b,k] = 1 for the boxes kept by nms_2d_faster (mode 0), nms_3d_faster (mode 1) or
+ *   nms_3d_faster_samecls (mode 2) of utils/nms.py:39-147 applied to the boxes with valid[b,k] != 0 (NULL = all),
+ *   scores (B,K) f32, classes (B,K) int64 (mode 2), fp64 arithmetic in numpy's expression order; equal scores are
+ *   ordered as by a stable sort.  K <= 512. */
+int spc_box_point_counts(const float *points, int point_stride, const double *corners, int B, int N, int K,
+                         int32_t *counts, void *stream);
+int spc_nms_boxes(const double *corners, const float *score, const int64_t *cls, const int32_t *valid, int B,
+                  int K, int mode, int old_type, double iou_threshold, int32_t *pick, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

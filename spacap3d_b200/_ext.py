@@ -419,3 +419,37 @@ def bn_relu_maxpool_train_backward(dpool, argmax, ymax, y, gamma, beta, mean, in
                   y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), invstd.data_ptr(), B, C,
                   npoint, nsample, dy.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _stream())
     return dy, dgamma, dbeta
+
+
+def box_point_counts(points, corners):
+    """points (B,N,>=3) f32, corners (B,K,8,3) f64 -> (B,K) int32 points inside each box
+    (ap_helper.py:69-79: extract_pc_in_box3d per predicted box)."""
+    _check(points, "points", torch.float32)
+    _check(corners, "corners", torch.float64)
+    _same_device(points, corners)
+    B, N, stride = points.shape
+    K = corners.shape[1]
+    counts = torch.empty((B, K), dtype=torch.int32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.call("spc_box_point_counts", points.data_ptr(), int(stride), corners.data_ptr(), B, N, K,
+                  counts.data_ptr(), _stream())
+    return counts
+
+
+def nms_boxes(corners, score, cls=None, valid=None, mode=2, old_type=False, iou_threshold=0.25):
+    """corners (B,K,8,3) f64, score (B,K) f32, cls (B,K) i64, valid (B,K) i32 -> pick (B,K) int32.
+    mode 0/1/2 = nms_2d_faster / nms_3d_faster / nms_3d_faster_samecls (utils/nms.py:39-147)."""
+    _check(corners, "corners", torch.float64)
+    _check(score, "score", torch.float32)
+    if cls is not None:
+        _check(cls, "cls", torch.int64)
+    if valid is not None:
+        _check(valid, "valid", torch.int32)
+    _same_device(corners, score)
+    B, K = score.shape
+    pick = torch.empty((B, K), dtype=torch.int32, device=score.device)
+    with torch.cuda.device(score.device):
+        _lib.call("spc_nms_boxes", corners.data_ptr(), score.data_ptr(),
+                  cls.data_ptr() if cls is not None else None, valid.data_ptr() if valid is not None else None,
+                  B, K, int(mode), int(bool(old_type)), float(iou_threshold), pick.data_ptr(), _stream())
+    return pick

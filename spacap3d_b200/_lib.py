@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -29,6 +29,8 @@ SIGNATURES = {
     "spc_ball_query_ex": [_p, _p, _i, _i, _i, _f, _i, _p, _p, ctypes.c_size_t, _p],
     "spc_group_points": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
+    "spc_box_point_counts": [_p, _i, _p, _i, _i, _i, _p, _p],
+    "spc_nms_boxes": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_double, _p, _p],
     "spc_bn_relu_train_forward": [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p],
     "spc_bn_relu_maxpool_train_forward": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                           ctypes.c_size_t, _p],
