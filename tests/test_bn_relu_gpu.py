@@ -1,6 +1,8 @@
 """Training-mode BatchNorm + ReLU kernels (csrc/bn_relu.cu) against torch.nn.BatchNorm2d + ReLU in fp32
 (the reference's pytorch_utils.Conv2d block, :11-36,39-64): forward values, running statistics,
 num_batches_tracked, input / affine gradients; then a whole SA module trained with and without the fusion."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -30,7 +32,7 @@ def _torch_ref(y, gamma, beta, rm, rv, momentum, eps, dz):
 def test_bn_relu_matches_torch(name):
     from spacap3d_b200 import _ext
     B, C, H, W = SHAPES[name]
-    g = torch.Generator(device="cpu").manual_seed(hash(name) % 1000)
+    g = torch.Generator(device="cpu").manual_seed(zlib.crc32(name.encode()) % 1000)   # hash() is salted per process
     y = torch.randn(B, C, H, W, generator=g)
     if name == "big_mean":
         y = y * 0.01 + 50.0
@@ -56,10 +58,20 @@ def test_bn_relu_matches_torch(name):
     torch.testing.assert_close(z, z_ref, rtol=tol, atol=tol)
     torch.testing.assert_close(rm, rm_ref, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(rv, rv_ref, rtol=1e-3 if name == "big_mean" else 1e-5, atol=1e-7)
+    # The ReLU mask is recomputed from y: an element whose normalised value is within rounding of 0 may land on
+    # the other side than in ATen (its gradient then differs by the full dz*gamma*invstd).  Compare dy away from
+    # the kink, and require the kink set to be tiny; the channel sums absorb the few flipped elements.
+    zlin = torch.nn.functional.batch_norm(y, None, None, gamma, beta, True, 0.0, eps)
+    stable = zlin.abs() > 50 * tol
+    assert (~stable).float().mean().item() < 200 * tol        # ~N(0,1) density around 0
     scale = max(1.0, dy_ref.abs().max().item())
-    torch.testing.assert_close(dy, dy_ref, rtol=10 * tol, atol=10 * tol * scale)
-    torch.testing.assert_close(dg, dg_ref, rtol=1e-4, atol=1e-4 * max(1.0, dg_ref.abs().max().item()))
-    torch.testing.assert_close(db, db_ref, rtol=1e-4, atol=1e-4 * max(1.0, db_ref.abs().max().item()))
+    torch.testing.assert_close(torch.where(stable, dy, dy_ref), dy_ref, rtol=10 * tol, atol=10 * tol * scale)
+    # channel sums: equal up to fp32 summation error plus whatever the elements at the kink can contribute
+    xhat = torch.nn.functional.batch_norm(y, None, None, None, None, True, 0.0, eps)
+    slack_g = ((dz * xhat).abs() * ~stable).sum(dim=(0, 2, 3))
+    slack_b = (dz.abs() * ~stable).sum(dim=(0, 2, 3))
+    assert ((dg - dg_ref).abs() <= slack_g + 1e-4 * max(1.0, dg_ref.abs().max().item())).all()
+    assert ((db - db_ref).abs() <= slack_b + 1e-4 * max(1.0, db_ref.abs().max().item())).all()
 
 
 def test_sa_module_training_step_same_with_and_without_fusion():
