@@ -41,7 +41,7 @@ CONFIG_ID = 2
 WORKLOAD = ("SpaCap3D xyz: batch 8 scenes x 40k pts per GPU, full detector forward "
             "(SA 2048/1024/512/256, FP1-2, voting, 256 proposals, box decode)")
 N_INPUT_SETS = 26        # distinct batches rotated through the timed loops: 26 x 5.12 MB = 133 MB > 126 MB L2
-N_STREAMS = 12           # CUDA-graph replay streams (batches are independent; FPS uses 64 of 148 SMs)
+N_STREAMS = 16           # CUDA-graph replay streams (batches are independent; FPS uses 64 of 148 SMs)
 
 
 # ------------------------------------------------------------------------------------------------
