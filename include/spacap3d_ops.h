@@ -247,6 +247,44 @@ int spc_box_point_counts(const float *points, int point_stride, const double *co
 int spc_nms_boxes(const double *corners, const float *score, const int64_t *cls, const int32_t *valid, int B,
                   int K, int mode, int old_type, double iou_threshold, int32_t *pick, void *stream);
 
+/* ---- input pipeline: device side of ScannetReferenceDataset.__getitem__, lib/dataset.py:291-531 ----
+ * The pre-processed scenes live in HBM as ONE packed vertex table verts (total_rows, vstride) f32 -- columns
+ * x y z r g b nx ny nz as written by data/scannet/batch_load_scannet_data.py:75-80 -- plus, optionally, a packed
+ * multiview table (total_rows, n_mv) f32 (the ENet features the reference reads per item from an h5py file,
+ * lib/dataset.py:321-328) and packed int32 instance / semantic label columns.  Batch item b refers to the scene whose
+ * first row is row0[b]; choices (B,P) int32 are row numbers RELATIVE to that scene (np.random.choice of
+ * utils/pc_utils.py:32-40, drawn on the host so that the reference's RNG stream is preserved).
+ *
+ * spc_scene_floor_height: out[0] = np.percentile(verts[:M, col], 100*quantile) with numpy >= 2.0 float32 semantics
+ *   (`quantile` is the float32 value np.float32(0.99)/np.float32(100) for lib/dataset.py:331); one CTA, radix select.
+ *   Call once per scene when it is loaded and cache the value.  Finite inputs only.
+ * spc_prepare_point_clouds: out (B,P,C_out) f32, C_out = 3 [+3 colour] [+3 normal] [+n_mv] [+1 height], in the
+ *   reference's channel order (lib/dataset.py:309-333).  colour = (rgb - mean)/256 in fp64 -> fp32 (:314);
+ *   height = z - floor_height[b] (fp32, BEFORE augmentation, :330-333; floor_height NULL = no height channel);
+ *   aug (B,32) f64 per item = [flip_x, flip_y, rotx(9), roty(9), rotz(9), translation(3)] (:366-404; NULL = no
+ *   augmentation): xyz is negated / multiplied by each 3x3 matrix in fp64 and ROUNDED TO fp32 after every step, as
+ *   numpy does when assigning into the float32 cloud; normals are not rotated (neither does the reference).
+ * spc_vote_labels: vote_label (B,P,9) f32 and vote_label_mask (B,P) int64 of lib/dataset.py:421-431 from the prepared
+ *   clouds (B,P,C): per instance id the bounding box of its sampled points, centre = 0.5*(min+max), vote = centre - x,
+ *   tiled 3x; an instance votes iff the semantic label of its first sampled point is in sem_mask (bit i = label i,
+ *   DC.nyu40ids).  Instance ids must be in [0, max_instances); others get no vote and set *overflow = 1 (nullable).
+ *   workspace: spc_vote_labels_workspace_bytes(B, max_instances) bytes.
+ * spc_augment_boxes: the same flips / rotations / translation applied to axis-aligned boxes (B,K,6) f64 =
+ *   centre + lengths (lib/dataset.py:369-404, rotate_aligned_boxes_along_axis,
+ *   data/scannet/model_util_scannet.py:47-82), fp64 throughout. */
+int spc_scene_floor_height(const float *verts, int M, int stride, int col, float quantile, float *out,
+                           void *stream);
+int spc_prepare_point_clouds(const float *verts, int vstride, const float *multiview, int n_mv,
+                             const int64_t *row0, const int32_t *choices, const float *floor_height,
+                             const double *aug, double mean_r, double mean_g, double mean_b, int B, int P,
+                             int use_color, int use_normal, float *out, void *stream);
+size_t spc_vote_labels_workspace_bytes(int B, int max_instances);
+int spc_vote_labels(const float *point_clouds, int C, const int32_t *instance_labels,
+                    const int32_t *semantic_labels, const int64_t *row0, const int32_t *choices, int B, int P,
+                    int max_instances, uint64_t sem_mask, float *vote_label, int64_t *vote_label_mask,
+                    int32_t *overflow, void *workspace, size_t workspace_bytes, void *stream);
+int spc_augment_boxes(const double *boxes, const double *aug, int B, int K, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -453,3 +453,92 @@ def nms_boxes(corners, score, cls=None, valid=None, mode=2, old_type=False, iou_
                   cls.data_ptr() if cls is not None else None, valid.data_ptr() if valid is not None else None,
                   B, K, int(mode), int(bool(old_type)), float(iou_threshold), pick.data_ptr(), _stream())
     return pick
+
+
+# ---- input pipeline (lib/dataset.py:291-531) ------------------------------------------------------
+
+def scene_floor_height(verts, col=2, quantile=None):
+    """verts (M,stride) f32 -> (1,) f32 = np.percentile(verts[:, col], 0.99) (lib/dataset.py:331)."""
+    import numpy as np
+    _check(verts, "verts", torch.float32)
+    _same_device(verts)
+    M, stride = verts.shape
+    if quantile is None:
+        quantile = float(np.float32(0.99) / np.float32(100))        # numpy's float32 quantile for a float32 column
+    out = torch.empty(1, dtype=torch.float32, device=verts.device)
+    with torch.cuda.device(verts.device):
+        _lib.call("spc_scene_floor_height", verts.data_ptr(), int(M), int(stride), int(col), float(quantile),
+                  out.data_ptr(), _stream())
+    return out
+
+
+def prepare_point_clouds(verts, row0, choices, multiview=None, floor_height=None, aug=None, mean_rgb=None,
+                         use_color=False, use_normal=False):
+    """Packed vertex table (rows,stride) f32 + row0 (B,) i64 + choices (B,P) i32 -> point_clouds (B,P,C) f32
+    (lib/dataset.py:309-335 and the augmentation of :366-404; `aug` (B,32) f64, see include/spacap3d_ops.h)."""
+    _check(verts, "verts", torch.float32)
+    _check(row0, "row0", torch.int64)
+    _check(choices, "choices", torch.int32)
+    others = [row0, choices]
+    n_mv = 0
+    if multiview is not None:
+        _check(multiview, "multiview", torch.float32)
+        n_mv = multiview.shape[1]
+        others.append(multiview)
+    if floor_height is not None:
+        _check(floor_height, "floor_height", torch.float32)
+        others.append(floor_height)
+    if aug is not None:
+        _check(aug, "aug", torch.float64)
+        if tuple(aug.shape) != (choices.shape[0], 32):
+            raise RuntimeError("aug must be (B,32)")
+        others.append(aug)
+    _same_device(verts, *others)
+    B, P = choices.shape
+    if use_color and mean_rgb is None:
+        raise RuntimeError("use_color needs mean_rgb")
+    mr = [float(v) for v in (mean_rgb if mean_rgb is not None else (0.0, 0.0, 0.0))]
+    C = 3 + (3 if use_color else 0) + (3 if use_normal else 0) + n_mv + (1 if floor_height is not None else 0)
+    out = torch.empty((B, P, C), dtype=torch.float32, device=verts.device)
+    with torch.cuda.device(verts.device):
+        _lib.call("spc_prepare_point_clouds", verts.data_ptr(), int(verts.shape[1]),
+                  multiview.data_ptr() if multiview is not None else None, int(n_mv), row0.data_ptr(),
+                  choices.data_ptr(), floor_height.data_ptr() if floor_height is not None else None,
+                  aug.data_ptr() if aug is not None else None, mr[0], mr[1], mr[2], B, P, int(bool(use_color)),
+                  int(bool(use_normal)), out.data_ptr(), _stream())
+    return out
+
+
+def vote_labels(point_clouds, instance_labels, semantic_labels, row0, choices, max_instances, sem_mask):
+    """-> vote_label (B,P,9) f32, vote_label_mask (B,P) i64, overflow (1,) i32   (lib/dataset.py:421-431)."""
+    _check(point_clouds, "point_clouds", torch.float32)
+    _check(instance_labels, "instance_labels", torch.int32)
+    _check(semantic_labels, "semantic_labels", torch.int32)
+    _check(row0, "row0", torch.int64)
+    _check(choices, "choices", torch.int32)
+    _same_device(point_clouds, instance_labels, semantic_labels, row0, choices)
+    B, P, C = point_clouds.shape
+    dev = point_clouds.device
+    votes = torch.empty((B, P, 9), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, P), dtype=torch.int64, device=dev)
+    overflow = torch.empty(1, dtype=torch.int32, device=dev)
+    nbytes = _lib.load().spc_vote_labels_workspace_bytes(B, int(max_instances))
+    ws = torch.empty(max(1, nbytes // 4), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("spc_vote_labels", point_clouds.data_ptr(), int(C), instance_labels.data_ptr(),
+                  semantic_labels.data_ptr(), row0.data_ptr(), choices.data_ptr(), B, P, int(max_instances),
+                  int(sem_mask), votes.data_ptr(), mask.data_ptr(), overflow.data_ptr(), ws.data_ptr(), nbytes,
+                  _stream())
+    return votes, mask, overflow
+
+
+def augment_boxes(boxes, aug):
+    """boxes (B,K,6) f64 + aug (B,32) f64 -> (B,K,6) f64   (lib/dataset.py:369-404)."""
+    _check(boxes, "boxes", torch.float64)
+    _check(aug, "aug", torch.float64)
+    _same_device(boxes, aug)
+    B, K, _ = boxes.shape
+    out = torch.empty_like(boxes)
+    with torch.cuda.device(boxes.device):
+        _lib.call("spc_augment_boxes", boxes.data_ptr(), aug.data_ptr(), B, K, out.data_ptr(), _stream())
+    return out

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -31,6 +31,11 @@ SIGNATURES = {
     "spc_group_points_grad": [_p, _p, _i, _i, _i, _i, _i, _p, _p],
     "spc_box_point_counts": [_p, _i, _p, _i, _i, _i, _p, _p],
     "spc_nms_boxes": [_p, _p, _p, _p, _i, _i, _i, _i, ctypes.c_double, _p, _p],
+    "spc_scene_floor_height": [_p, _i, _i, _i, _f, _p, _p],
+    "spc_prepare_point_clouds": [_p, _i, _p, _i, _p, _p, _p, _p, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                 _i, _i, _i, _i, _p, _p],
+    "spc_vote_labels": [_p, _i, _p, _p, _p, _p, _i, _i, _i, ctypes.c_uint64, _p, _p, _p, _p, ctypes.c_size_t, _p],
+    "spc_augment_boxes": [_p, _p, _i, _i, _p, _p],
     "spc_bn_relu_train_forward": [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, ctypes.c_size_t, _p],
     "spc_bn_relu_maxpool_train_forward": [_p, _p, _p, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p,
                                           ctypes.c_size_t, _p],
@@ -76,6 +81,8 @@ def load():
     lib.spc_group_points_grad_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_bn_relu_workspace_bytes.argtypes = [_i]
     lib.spc_bn_relu_workspace_bytes.restype = ctypes.c_size_t
+    lib.spc_vote_labels_workspace_bytes.argtypes = [_i, _i]
+    lib.spc_vote_labels_workspace_bytes.restype = ctypes.c_size_t
     lib.spc_fps_workspace_bytes.argtypes = [_i, _i, _i]
     lib.spc_fps_workspace_bytes.restype = ctypes.c_size_t
     for name, argtypes in SIGNATURES.items():

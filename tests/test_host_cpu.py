@@ -26,7 +26,8 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared - {"spc_abi_version", "spc_last_error", "spc_fps_workspace_bytes", "spc_ball_query_workspace_bytes",
-                       "spc_group_points_grad_workspace_bytes", "spc_bn_relu_workspace_bytes"} == set(_lib.SIGNATURES)
+                       "spc_group_points_grad_workspace_bytes", "spc_bn_relu_workspace_bytes",
+                       "spc_vote_labels_workspace_bytes"} == set(_lib.SIGNATURES)
     assert lib.spc_abi_version() == _lib.ABI_VERSION
 
 
