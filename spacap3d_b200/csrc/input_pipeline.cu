@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(FH_THREADS) floor_height_kernel(const float *_
 // point-cloud assembly.  aug (B,32) f64 per item: [flip_x, flip_y, Rx(9), Ry(9), Rz(9), t(3)], row-major matrices as
 // returned by rotx/roty/rotz (utils/pc_utils.py:282-320).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int PP_ROWS = 256;      // rows per CTA = threads per CTA
-constexpr int PP_SMALL = 10;      // xyz + rgb + normal + height
+// rows per CTA (template): the CTA's output span (PP_ROWS x C_out floats) is staged in shared memory; 64 with multiview
+// features (35 KB tiles, 6 CTAs / SM), 256 without (one thread per row in phase 1)
+constexpr int PP_THREADS = 256;
 
 struct PrepArgs {
   const float *verts; int vstride;
@@ -119,27 +120,34 @@ __device__ __forceinline__ float rot_row(const double *R, float x, float y, floa
   return (float)fma((double)z, R[2], fma((double)y, R[1], (double)x * R[0]));
 }
 
-__global__ void __launch_bounds__(PP_ROWS) prepare_points_kernel(PrepArgs a) {
-  __shared__ float s_small[PP_ROWS][PP_SMALL + 1];
+// Phase 1: one thread per row computes the <= 10 "small" channels (fp64 where numpy uses fp64) into the tile.
+// Phase 2: one warp per row gathers the 4*n_mv-byte multiview row with 16-byte loads (eight rows in flight per warp).
+// Phase 3: the tile -- a contiguous span of the output -- leaves with ONE bulk TMA store (cp.async.bulk.global.shared),
+//          or a coalesced scalar loop when the span is not 16-byte aligned.
+template <int PP_ROWS>
+__global__ void __launch_bounds__(PP_THREADS) prepare_points_kernel(PrepArgs a) {
+  extern __shared__ __align__(128) float s_tile[];                    // [PP_ROWS][C_out]
   __shared__ int64_t s_src[PP_ROWS];
   const int b = blockIdx.y;
   const int r0 = blockIdx.x * PP_ROWS;
   const int nrows = min(PP_ROWS, a.P - r0);
   const int t = threadIdx.x;
+  const int C = a.C_out, n_mv = a.n_mv;
   const int n_pre = 3 + (a.use_color ? 3 : 0) + (a.use_normal ? 3 : 0);
   if (t < nrows) {
     const int64_t src = a.row0[b] + (int64_t)__ldg(a.choices + (size_t)b * a.P + r0 + t);
     s_src[t] = src;
+    float *o = s_tile + t * C;
     const float *v = a.verts + (size_t)src * a.vstride;
     float x = __ldg(v), y = __ldg(v + 1), z = __ldg(v + 2);
     int c = 3;
     if (a.use_color) {                      // (rgb - MEAN_COLOR_RGB) / 256.0 in float64 -> float32 (dataset.py:314)
-      for (int k = 0; k < 3; ++k) s_small[t][c++] = (float)(((double)__ldg(v + 3 + k) - a.mean_rgb[k]) / 256.0);
+      for (int k = 0; k < 3; ++k) o[c++] = (float)(((double)__ldg(v + 3 + k) - a.mean_rgb[k]) / 256.0);
     }
     if (a.use_normal) {                     // copied as stored; the reference does not rotate normals (dataset.py:317-319)
-      for (int k = 0; k < 3; ++k) s_small[t][c++] = __ldg(v + 6 + k);
+      for (int k = 0; k < 3; ++k) o[c++] = __ldg(v + 6 + k);
     }
-    if (a.use_height) s_small[t][c] = __fsub_rn(z, __ldg(a.floor_height + b));   // before augmentation (dataset.py:330-333)
+    if (a.use_height) o[n_pre + n_mv] = __fsub_rn(z, __ldg(a.floor_height + b));   // before augmentation (dataset.py:330-333)
     if (a.aug != nullptr) {
       const double *p = a.aug + (size_t)b * 32;
       if (p[0] != 0.0) x = -x;              // flip along the YZ plane (dataset.py:369)
@@ -154,22 +162,50 @@ __global__ void __launch_bounds__(PP_ROWS) prepare_points_kernel(PrepArgs a) {
       y = (float)((double)y + p[30]);
       z = (float)((double)z + p[31]);
     }
-    s_small[t][0] = x; s_small[t][1] = y; s_small[t][2] = z;
+    o[0] = x; o[1] = y; o[2] = z;
   }
   __syncthreads();
-  // the CTA's output rows are one contiguous span: write it flat, fully coalesced; multiview columns are gathered
-  // as 4*n_mv-byte row segments (each consecutive run of lanes reads consecutive floats of one source row)
-  float *o = a.out + ((size_t)b * a.P + r0) * a.C_out;
-  const int total = nrows * a.C_out;
-  const int C = a.C_out, n_mv = a.n_mv;
-#pragma unroll 4
-  for (int i = t; i < total; i += PP_ROWS) {
-    const int row = i / C, c = i - row * C;
-    float val;
-    if (c < n_pre) val = s_small[row][c];
-    else if (c < n_pre + n_mv) val = __ldg(a.multiview + (size_t)s_src[row] * n_mv + (c - n_pre));
-    else val = s_small[row][n_pre];
-    __stcs(o + i, val);
+  if (n_mv > 0) {
+    const int warp = t >> 5, lane = t & 31;
+    constexpr int NW = PP_THREADS / 32;
+    const bool vec = (n_mv & 3) == 0 && ((uintptr_t)a.multiview & 15) == 0;
+    if (vec) {
+      const int nv = n_mv >> 2;                                       // float4 per row
+      for (int q0 = lane; q0 < nv; q0 += 32) {
+        float4 val[PP_ROWS / NW];
+#pragma unroll
+        for (int k = 0; k < PP_ROWS / NW; ++k) {
+          const int row = warp + k * NW;
+          if (row < nrows) val[k] = __ldcs(reinterpret_cast<const float4 *>(a.multiview + (size_t)s_src[row] * n_mv) + q0);
+        }
+#pragma unroll
+        for (int k = 0; k < PP_ROWS / NW; ++k) {
+          const int row = warp + k * NW;
+          if (row < nrows) {
+            float *o = s_tile + row * C + n_pre + 4 * q0;
+            o[0] = val[k].x; o[1] = val[k].y; o[2] = val[k].z; o[3] = val[k].w;
+          }
+        }
+      }
+    } else {
+      for (int row = warp; row < nrows; row += NW)
+        for (int c = lane; c < n_mv; c += 32)
+          s_tile[row * C + n_pre + c] = __ldg(a.multiview + (size_t)s_src[row] * n_mv + c);
+    }
+    __syncthreads();
+  }
+  float *o = a.out + ((size_t)b * a.P + r0) * C;
+  const unsigned bytes = (unsigned)nrows * C * 4u;
+  if ((((uintptr_t)o | bytes) & 15) == 0) {
+    if (t == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o),
+                   "r"((unsigned)__cvta_generic_to_shared(s_tile)), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the copy's reads
+    }
+  } else {
+    for (int i = t; i < nrows * C; i += PP_THREADS) __stcs(o + i, s_tile[i]);
   }
 }
 
@@ -352,8 +388,17 @@ extern "C" int spc_prepare_point_clouds(const float *verts, int vstride, const f
   a.P = P; a.use_color = use_color != 0; a.use_normal = use_normal != 0; a.use_height = floor_height != nullptr;
   a.C_out = 3 + (a.use_color ? 3 : 0) + (a.use_normal ? 3 : 0) + n_mv + (a.use_height ? 1 : 0);
   a.out = out;
-  dim3 grid(ceil_div(P, PP_ROWS), B);
-  prepare_points_kernel<<<grid, PP_ROWS, 0, (cudaStream_t)stream>>>(a);
+  const int rows = n_mv > 0 ? 64 : 256;
+  const size_t smem = (size_t)rows * a.C_out * sizeof(float);
+  SPC_CHECK_ARG(smem <= 200 * 1024, "spc_prepare_point_clouds: %d output channels exceed the shared-memory tile", a.C_out);
+  dim3 grid(ceil_div(P, rows), B);
+  if (n_mv > 0) {
+    if (smem > 48 * 1024)
+      SPC_CUDA(cudaFuncSetAttribute(prepare_points_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prepare_points_kernel<64><<<grid, PP_THREADS, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    prepare_points_kernel<256><<<grid, PP_THREADS, smem, (cudaStream_t)stream>>>(a);
+  }
   SPC_LAUNCH_CHECK("prepare_points_kernel");
   return SPC_OK;
 }

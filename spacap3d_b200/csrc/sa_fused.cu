@@ -203,22 +203,33 @@ constexpr int SA_W0_STRIDE = 20;    // floats per channel row of the inline laye
 // In-line layer 0 with exactly NIN inputs: in = [(p-c)/r (3), features (Cf), 1 (bias)], NIN = 4+Cf.
 // Weights sit in shared memory transposed per 8-channel chunk, sW0t[kc][k][8], so that one input
 // updates 8 accumulators from two broadcast 16-byte reads and no FMA is spent on padding.
-template <int NIN>
-__device__ __forceinline__ void sa_inline_load(const SaFusedParams &p, int tile, int r, int i, int rows_per_scene,
-                                               float inv_r, float (&in)[NIN]) {
-  const long long R = (long long)tile * SA_ROWS + r;
-  const int b = (int)(R / rows_per_scene);
-  const int j = (int)(R - (long long)b * rows_per_scene) / p.ns;
+// The loads of a row are ISSUED a tile ahead (raw values stay in registers) and only FINISHED -- subtraction, scaling --
+// when the tile is computed: doing the arithmetic at issue time made every producer thread wait for its own gather
+// (ncu: stall_long_sb on the subtraction was as large as the whole layer-0 math).  Tiles never straddle scenes
+// (npoint*nsample % 128 == 0 is checked at launch), so scene / centre follow from 32-bit arithmetic on the tile index.
+template <int NIN, int NS>
+__device__ __forceinline__ void sa_inline_issue(const SaFusedParams &p, int tile, int r, int i, int tiles_per_scene,
+                                                float (&raw)[NIN + 2]) {
+  const int b = tile / tiles_per_scene;
+  const int j = ((tile - b * tiles_per_scene) * SA_ROWS + r) / NS;
   const float *pp = p.xyz + ((size_t)b * p.n + i) * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
-  // (p - c) / r as a multiplication by 1/r (this path feeds a bf16 MLP: a 1-ulp difference to the
-  // reference's true division is far below the rounding of the next step)
-  in[0] = (__ldg(pp + 0) - __ldg(cc + 0)) * inv_r;
-  in[1] = (__ldg(pp + 1) - __ldg(cc + 1)) * inv_r;
-  in[2] = (__ldg(pp + 2) - __ldg(cc + 2)) * inv_r;
+  raw[0] = __ldg(pp + 0); raw[1] = __ldg(pp + 1); raw[2] = __ldg(pp + 2);
+  raw[3] = __ldg(cc + 0); raw[4] = __ldg(cc + 1); raw[5] = __ldg(cc + 2);
   const float *fp = p.feat + (size_t)b * p.Cf * p.n + i;
 #pragma unroll
-  for (int f = 3; f < NIN - 1; ++f) in[f] = __ldg(fp + (size_t)(f - 3) * p.n);
+  for (int f = 3; f < NIN - 1; ++f) raw[3 + f] = __ldg(fp + (size_t)(f - 3) * p.n);
+}
+
+template <int NIN>
+__device__ __forceinline__ void sa_inline_finish(const float (&raw)[NIN + 2], float inv_r, float (&in)[NIN]) {
+  // (p - c) / r as a multiplication by 1/r (this path feeds a bf16 MLP: a 1-ulp difference to the
+  // reference's true division is far below the rounding of the next step)
+  in[0] = (raw[0] - raw[3]) * inv_r;
+  in[1] = (raw[1] - raw[4]) * inv_r;
+  in[2] = (raw[2] - raw[5]) * inv_r;
+#pragma unroll
+  for (int f = 3; f < NIN - 1; ++f) in[f] = raw[3 + f];
   in[NIN - 1] = 1.f;                                  // the folded bias rides along as the last "input"
 }
 
@@ -252,18 +263,17 @@ __device__ __forceinline__ void sa_inline_compute(const float (&in)[NIN], int r,
 // coalesced request (2 L1 wavefronts per row instead of 16+ with lane = row), 16 rows in flight per
 // warp.  Lane = 8 consecutive channels of one row: one 16-byte load, 8 x (3 FMA + add + relu) with
 // this lane's xyz weights / bias in registers, one 16-byte store into the swizzled H1.
-template <int C1>
+template <int C1, int NS>
 __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, int tile, int warp, int lane,
                                                         int my_idx, const float (&wx)[8][3], const float (&wb)[8],
-                                                        uint8_t *sH1, int rows_per_scene) {
+                                                        uint8_t *sH1, int tiles_per_scene) {
   constexpr int LPR = C1 / 8;                 // lanes per row (8 bf16 = 16 bytes each)
   constexpr int RPI = 32 / LPR;               // rows per warp-wide load
   constexpr int NPASS = 16 / RPI;             // a warp owns 16 rows of the tile
   const int kc = lane % LPR;
   const int sub = lane / LPR;
-  const long long R0 = (long long)tile * SA_ROWS + warp * 16;
-  const int b = (int)(R0 / rows_per_scene);
-  const int j = (int)(R0 - (long long)b * rows_per_scene) / p.ns;      // the 16 rows share one centre (ns >= 16)
+  const int b = tile / tiles_per_scene;                                // tiles never straddle scenes
+  const int j = ((tile - b * tiles_per_scene) * SA_ROWS + warp * 16) / NS;   // the 16 rows share one centre (ns >= 16)
   const __nv_bfloat16 *Gb = p.G + (size_t)b * p.n * C1 + 8 * kc;
   const float *Pb = p.xyz + (size_t)b * p.n * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
@@ -403,7 +413,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int rows_per_scene = p.np * p.ns;
+  const int tiles_per_scene = (p.np * NS) / SA_ROWS;
   const int nt = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   if (warp < SAP_PROD_WARPS) {
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         const int my_idx = i_next;
         if (k + 1 < nt) i_next = load_idx(tile + (int)gridDim.x);              // a tile ahead
         mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);           // MMA1(k-2) has consumed H1[s]
-        sa_produce_proj_rowwise<C1>(p, tile, warp, lane, my_idx, wx, wb, sH1 + s * L::H1_BYTES, rows_per_scene);
+        sa_produce_proj_rowwise<C1, NS>(p, tile, warp, lane, my_idx, wx, wb, sH1 + s * L::H1_BYTES, tiles_per_scene);
         fence_proxy_async_smem();
         mbarrier_arrive(&h1_full[s]);
       }
@@ -446,18 +456,17 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
       auto run = [&](auto nin_tag) {
         constexpr int NIN = decltype(nin_tag)::value;
         const int t0 = (int)blockIdx.x, dt = (int)gridDim.x;
-        float in_next[NIN];
+        float raw_next[NIN + 2];
         int i1 = __ldg(p.idx + (long long)t0 * SA_ROWS + r);
-        sa_inline_load<NIN>(p, t0, r, i1, rows_per_scene, inv_r, in_next);
+        sa_inline_issue<NIN, NS>(p, t0, r, i1, tiles_per_scene, raw_next);
         i1 = nt > 1 ? __ldg(p.idx + (long long)(t0 + dt) * SA_ROWS + r) : 0;
         for (int k = 0; k < nt; ++k) {
           const int s = k & 1, n = k >> 1;
           const int tile = t0 + k * dt;
           float in[NIN];
-#pragma unroll
-          for (int q = 0; q < NIN; ++q) in[q] = in_next[q];
+          sa_inline_finish<NIN>(raw_next, inv_r, in);
           if (k + 1 < nt) {
-            sa_inline_load<NIN>(p, tile + dt, r, i1, rows_per_scene, inv_r, in_next);
+            sa_inline_issue<NIN, NS>(p, tile + dt, r, i1, tiles_per_scene, raw_next);
             if (k + 2 < nt) i1 = __ldg(p.idx + (long long)(tile + 2 * dt) * SA_ROWS + r);
           }
           mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
@@ -564,9 +573,9 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
     // =============================== EPILOGUE 2: D2 -> max-pool -> out ==========================
     const int q = warp & 3;
     for (int k = 0; k < nt; ++k) {
-      const long long R0 = (long long)((int)blockIdx.x + k * (int)gridDim.x) * SA_ROWS;
-      const int b = (int)(R0 / rows_per_scene);
-      const int j0 = (int)((R0 - (long long)b * rows_per_scene) / NS);   // first centre of the tile
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const int b = tile / tiles_per_scene;
+      const int j0 = ((tile - b * tiles_per_scene) * SA_ROWS) / NS;      // first centre of the tile
 #pragma unroll
       for (int h = 0; h < NB; ++h) {
         const int u = k * NB + h, st = u & 1, nu = u >> 1;

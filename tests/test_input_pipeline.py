@@ -85,7 +85,10 @@ def test_device_batch_equals_reference(name):
     """Two items of the same scene with different draws through DeviceSceneStore.make_batch == the reference's
     __getitem__ statements (golden) for item 0 and the numpy oracle for item 1."""
     c = cases_input.case(name)
-    store = _store([cases_input.case("replace_eval"), c])                    # the scene is NOT first in the table
+    filler = cases_input.case("replace_eval")                                # the scene is NOT first in the table
+    if c["use_multiview"]:
+        filler["multiview"] = np.ones((filler["verts"].shape[0], 128), np.float32)
+    store = _store([filler, c])
     d0 = _draw(c)
     d1 = ip.draw_item(np.random.RandomState(c["seed"] + 100), c["verts"].shape[0], c["P"], c["augment"])
     out = store.make_batch(["s1", "s1"], [d0, d1], use_color=c["use_color"], use_normal=c["use_normal"],
@@ -146,3 +149,20 @@ def test_device_batch_full_size_properties():
                              want_votes=False)
     np.testing.assert_array_equal(eval_out["point_clouds"][0, :, :3].cpu().numpy(),
                                   v[eval_out["choices"][0].cpu().numpy(), :3])
+
+
+@pytest.mark.gpu
+def test_device_sampler_draws_valid_subsets():
+    ch = ip.draw_batch_device([5000, 1500, 3000], 2000, generator=torch.Generator("cuda").manual_seed(1)).cpu().numpy()
+    assert ch.shape == (3, 2000) and ch.dtype == np.int32
+    for row, m in zip(ch, (5000, 1500, 3000)):
+        assert row.min() >= 0 and row.max() < m
+    assert len(np.unique(ch[0])) == 2000 and len(np.unique(ch[2])) == 2000      # without replacement when M >= P
+    assert len(np.unique(ch[1])) < 1500                                        # with replacement when M < P
+
+
+def test_store_rejects_missing_multiview():
+    st = ip.DeviceSceneStore("cpu")
+    st.multiview = None
+    with pytest.raises(RuntimeError, match="multiview"):
+        st.make_batch([], [], use_multiview=True)
