@@ -161,3 +161,28 @@ def test_graphed_pipeline_equals_eager():
         _lib.call("spc_set_fps_cull", 0)
         _lib.call("spc_set_fps_cluster", 0)
         _lib.call("spc_set_sa_min_tiles", 0)
+
+
+@pytest.mark.parametrize("name,kw,dim", [
+    ("xyz_only", dict(use_height=False), 0),
+    ("rgb_normal_height", dict(use_color=True, use_normal=True), 7),            # BASELINE configs[2]
+    ("multiview_normal_height", dict(use_multiview=True, use_normal=True), 132),  # BASELINE configs[3]
+])
+def test_detector_other_feature_configs(name, kw, dim):
+    """The other input layouts of BASELINE.json (parity cases, not bench lines): sampling / grouping indices
+    bit-exact, features within the bf16 tolerance of the fp32 reference op sequence."""
+    from spacap3d_b200.detector import VoteNetDetector
+    from spacap3d_b200.scenes import make_scene
+    torch.manual_seed(1)
+    model = VoteNetDetector(input_feature_dim=dim).to(DEV).eval()
+    _randomize_bn(model, 21)
+    pc = torch.from_numpy(np.stack([make_scene(51, 20000, **kw), make_scene(52, 20000, **kw)], 0)).to(DEV)
+    assert pc.shape[2] == 3 + dim
+    with torch.no_grad():
+        fast = model({"point_clouds": pc})
+        with fp32_reference():
+            ref = model({"point_clouds": pc})
+    for k in ("sa1_inds", "sa2_inds", "sa1_xyz", "sa4_xyz", "seed_inds"):
+        assert torch.equal(fast[k], ref[k]), k
+    for k, tol in (("sa1_features", 1e-2), ("sa4_features", 2e-2), ("fp2_features", 3e-2), ("vote_features", 3e-2)):
+        assert _rel(fast[k], ref[k]) <= tol, (k, _rel(fast[k], ref[k]))
