@@ -354,6 +354,29 @@ __device__ __forceinline__ void mbarrier_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory");
 }
 
+// Row-major bf16 weights (ROWS, 8*KCH) -> the swizzled UMMA layout in shared memory; 8 x 16-byte loads in flight
+// per thread.
+template <int ROWS, int KCH, int NT>
+__device__ __forceinline__ void sa_stage_weights(uint8_t *dst, const __nv_bfloat16 *src, int t) {
+  constexpr int N = ROWS * KCH;
+  for (int base = 0; base < N; base += NT * 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * NT + t;
+      if (e < N) v[u] = __ldg(reinterpret_cast<const uint4 *>(src) + e);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * NT + t;
+      if (e < N) {
+        const int r = e / KCH, kc = e - r * KCH;
+        *reinterpret_cast<uint4 *>(dst + sw128_off(r, kc, ROWS)) = v[u];
+      }
+    }
+  }
+}
+
 template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
 __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaFusedParams p) {
   using L = SaPipeSmem<C1, C2, C3>;
@@ -374,6 +397,10 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
   const int K0 = 3 + p.Cf;
 
   // ---- one-time setup ---------------------------------------------------------------------------
+  // Only the barriers and the TMEM allocation are needed by everybody.  The 24-96 KB of folded weights are staged
+  // by the NON-producer warps (all loads of a pass issued before the first store: one L2 round trip per pass
+  // instead of one per element) while the producers already gather and compute their first tile; ncu had the
+  // serial staging + its barrier at ~20 % of the SA2 kernel's samples and more for the smaller layers.
   if (warp == 8) tmem_alloc(&tmem_base_smem, L::TMEM_COLS);
   if (tid == 0) {
 #pragma unroll
@@ -389,29 +416,28 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int e = tid; e < C2 * (C1 / 8); e += SAP_THREADS) {
-    const int r = e / (C1 / 8), kc = e - r * (C1 / 8);
-    *reinterpret_cast<uint4 *>(sW1 + sw128_off(r, kc, C2)) =
-        __ldg(reinterpret_cast<const uint4 *>(p.W1 + (size_t)r * C1 + kc * 8));
-  }
-  for (int e = tid; e < C3 * (C2 / 8); e += SAP_THREADS) {
-    const int r = e / (C2 / 8), kc = e - r * (C2 / 8);
-    *reinterpret_cast<uint4 *>(sW2 + sw128_off(r, kc, C3)) =
-        __ldg(reinterpret_cast<const uint4 *>(p.W2 + (size_t)r * C2 + kc * 8));
-  }
-  for (int e = tid; e < C2; e += SAP_THREADS) sB1[e] = __ldg(p.b1 + e);
-  if (!MODE_PROJ) {
-    // sW0t[kc][k][c8]: weight of input k for channel kc*8+c8; k == K0 holds the folded bias
-    for (int e = tid; e < C1 * SA_W0_STRIDE; e += SAP_THREADS) {
-      const int kc = e / (SA_W0_STRIDE * 8), rem = e - kc * (SA_W0_STRIDE * 8);
-      const int k = rem >> 3, c = kc * 8 + (rem & 7);
-      sW0[e] = k < K0 ? __ldg(p.W0 + (size_t)c * K0 + k) : (k == K0 ? __ldg(p.b0 + c) : 0.f);
-    }
-  }
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp < SAP_PROD_WARPS) {
+    if (!MODE_PROJ) {
+      // sW0t[kc][k][c8]: weight of input k for channel kc*8+c8; k == K0 holds the folded bias
+      for (int e = tid; e < C1 * SA_W0_STRIDE; e += SAP_PROD_WARPS * 32) {
+        const int kc = e / (SA_W0_STRIDE * 8), rem = e - kc * (SA_W0_STRIDE * 8);
+        const int k = rem >> 3, c = kc * 8 + (rem & 7);
+        sW0[e] = k < K0 ? __ldg(p.W0 + (size_t)c * K0 + k) : (k == K0 ? __ldg(p.b0 + c) : 0.f);
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(SAP_PROD_WARPS * 32) : "memory");
+    }
+  } else {
+    constexpr int NT = SAP_THREADS - SAP_PROD_WARPS * 32;     // 288 staging threads
+    const int t = tid - SAP_PROD_WARPS * 32;
+    sa_stage_weights<C2, C1 / 8, NT>(sW1, p.W1, t);
+    sa_stage_weights<C3, C2 / 8, NT>(sW2, p.W2, t);
+    for (int e = t; e < C2; e += NT) sB1[e] = __ldg(p.b1 + e);
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+  }
   const uint32_t tmem_base = tmem_base_smem;
   const int tiles_per_scene = (p.np * NS) / SA_ROWS;
   const int nt = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
