@@ -35,8 +35,46 @@ def timeit(fn, iters, flush):
     return statistics.median(ts), min(ts)
 
 
+def timeit_graph(fn, iters, flush, reps=8):
+    """Launch-overhead-free timing for ops that take a few microseconds: [flush, fn] x reps captured in one CUDA
+    graph, minus the same graph without fn.  Returns (per-call ms, per-call ms) like timeit()."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+
+    def capture(with_fn):
+        g = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                flush()
+                if with_fn:
+                    fn()
+        return g
+
+    ga, gb = capture(True), capture(False)
+
+    def run(g):
+        ts = []
+        for _ in range(max(3, iters // 2)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    run(ga), run(gb)
+    d = max(run(ga) - run(gb), 0.0) / reps
+    return d, d
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--graph", action="store_true",
+                    help="time OUR ops inside a CUDA graph (no host launch gap); the reference ext stays eager")
     ap.add_argument("--ops", default="fps,ball_query,group,interp,three_nn")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=15)
@@ -45,6 +83,7 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
+    timeit_ours = timeit_graph if args.graph else timeit
     ref = None
     if not args.no_ref:
         try:
@@ -81,13 +120,13 @@ def main():
     if "fps" in ops:
         for (pts, _, npoint, _, _) in levels:
             n = pts.shape[1]
-            o = timeit(lambda: _ext.furthest_point_sampling(pts, npoint), args.iters, flush)
+            o = timeit_ours(lambda: _ext.furthest_point_sampling(pts, npoint), args.iters, flush)
             t = timeit(lambda: ref.furthest_point_sampling(pts, npoint), max(3, args.iters // 3), flush) if ref else None
             rec("fps", [B, n, npoint], o, t, extra={"us_per_round": round(o[0] * 1e3 / (npoint - 1), 4)})
     if "ball_query" in ops:
         for (pts, new_xyz, npoint, r, ns) in levels:
             n = pts.shape[1]
-            o = timeit(lambda: _ext.ball_query(new_xyz, pts, r, ns), args.iters, flush)
+            o = timeit_ours(lambda: _ext.ball_query(new_xyz, pts, r, ns), args.iters, flush)
             t = timeit(lambda: ref.ball_query(new_xyz, pts, r, ns), max(3, args.iters // 3), flush) if ref else None
             rec("ball_query", [B, n, npoint, r, ns], o, t, B * (12 * n + 12 * npoint + 4 * npoint * ns))
     if "group" in ops:
@@ -96,28 +135,28 @@ def main():
             n = pts.shape[1]
             idx = _ext.ball_query(new_xyz, pts, r, ns)
             feats = torch.randn(B, C, n, device=dev)
-            o = timeit(lambda: _ext.group_points(feats, idx), args.iters, flush)
+            o = timeit_ours(lambda: _ext.group_points(feats, idx), args.iters, flush)
             t = timeit(lambda: ref.group_points(feats, idx), max(3, args.iters // 3), flush) if ref else None
             rec("group_points", [B, C, n, npoint, ns], o, t, 4 * B * (C * n + npoint * ns + C * npoint * ns))
             g = torch.randn(B, C, npoint, ns, device=dev)
-            o = timeit(lambda: _ext.group_points_grad(g, idx, n), args.iters, flush)
+            o = timeit_ours(lambda: _ext.group_points_grad(g, idx, n), args.iters, flush)
             t = timeit(lambda: ref.group_points_grad(g, idx, n), max(3, args.iters // 3), flush) if ref else None
             rec("group_points_grad", [B, C, n, npoint, ns], o, t, 4 * B * (C * n + npoint * ns + C * npoint * ns))
     if "three_nn" in ops or "interp" in ops:
         for (n, m) in ((512, 256), (1024, 512)):
             unknown = levels[3][0] if n == 512 else levels[2][0]
             known = levels[3][1] if n == 512 else levels[2][1]
-            o = timeit(lambda: _ext.three_nn(unknown, known), args.iters, flush)
+            o = timeit_ours(lambda: _ext.three_nn(unknown, known), args.iters, flush)
             t = timeit(lambda: ref.three_nn(unknown, known), max(3, args.iters // 3), flush) if ref else None
             rec("three_nn", [B, n, m], o, t, B * (12 * (n + m) + 24 * n))
             d2, idx = _ext.three_nn(unknown, known)
             w = torch.rand(B, n, 3, device=dev)
             feats = torch.randn(B, 256, m, device=dev)
-            o = timeit(lambda: _ext.three_interpolate(feats, idx, w), args.iters, flush)
+            o = timeit_ours(lambda: _ext.three_interpolate(feats, idx, w), args.iters, flush)
             t = timeit(lambda: ref.three_interpolate(feats, idx, w), max(3, args.iters // 3), flush) if ref else None
             rec("three_interpolate", [B, 256, m, n], o, t, 4 * B * (256 * m + 6 * n + 256 * n))
             g = torch.randn(B, 256, n, device=dev)
-            o = timeit(lambda: _ext.three_interpolate_grad(g, idx, w, m), args.iters, flush)
+            o = timeit_ours(lambda: _ext.three_interpolate_grad(g, idx, w, m), args.iters, flush)
             t = timeit(lambda: ref.three_interpolate_grad(g, idx, w, m), max(3, args.iters // 3), flush) if ref else None
             rec("three_interpolate_grad", [B, 256, n, m], o, t, 4 * B * (256 * n + 6 * n + 256 * m))
     if args.json:
