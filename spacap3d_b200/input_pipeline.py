@@ -80,13 +80,15 @@ def draw_batch_device(counts, num_points, generator=None, device="cuda"):
     cnt = torch.tensor(counts, device=device)
     keys = torch.rand((len(counts), M), generator=generator, device=device)
     keys.masked_fill_(torch.arange(M, device=device)[None, :] >= cnt[:, None], 2.0)    # rows beyond the scene sort last
-    perm = keys.argsort(dim=1)[:, :num_points]
+    perm = keys.argsort(dim=1)
+    if M < num_points:                                                                # every scene is too small
+        perm = torch.nn.functional.pad(perm, (0, num_points - M))
+    choices = perm[:, :num_points]
     if min(counts) < num_points:                                                      # replace=True for small scenes
         with_rep = (torch.rand((len(counts), num_points), generator=generator, device=device) * cnt[:, None]).long()
         with_rep = torch.minimum(with_rep, cnt[:, None] - 1)
-        perm = torch.where((cnt < num_points)[:, None], with_rep, perm[:, :num_points] if perm.shape[1] == num_points
-                           else torch.nn.functional.pad(perm, (0, num_points - perm.shape[1])))
-    return perm.to(torch.int32).contiguous()
+        choices = torch.where((cnt < num_points)[:, None], with_rep, choices)
+    return choices.to(torch.int32).contiguous()
 
 
 class DeviceSceneStore:
