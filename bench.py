@@ -171,6 +171,9 @@ ALGO_BYTES = {
     # fused SA fwd = 12n + 4*C*n + 4*np*ns + 4*C_out*np per scene (C = table width actually read)
     "spc_sa_fused_forward": lambda a: a[13] * (12 * a[14] + (2 * a[17] if a[3] else 4 * a[7]) * a[14]
                                                + 4 * a[15] * a[16] + 4 * a[19] * a[15]),
+    # _ex = same arguments with (W0_host, b0_host) inserted after b0: everything from Cf on moves by two
+    "spc_sa_fused_forward_ex": lambda a: a[15] * (12 * a[16] + (2 * a[19] if a[3] else 4 * a[9]) * a[16]
+                                                  + 4 * a[17] * a[18] + 4 * a[21] * a[17]),
 }
 # algorithmic FLOPs (2 * sum_l C_l*C_{l+1} * np*ns) of the MLP a fused launch replaces;
 # C_0 = 3 + input channels is not known to the projected form, so only layers 1,2 (the tcgen05
@@ -178,8 +181,11 @@ ALGO_BYTES = {
 ALGO_FLOPS = {
     "spc_sa_fused_forward": lambda a: 2 * a[13] * a[15] * a[16] * (
         a[17] * a[18] + a[18] * a[19] + (3 if a[3] else 3 + a[7]) * a[17]),
+    "spc_sa_fused_forward_ex": lambda a: 2 * a[15] * a[17] * a[18] * (
+        a[19] * a[20] + a[20] * a[21] + (3 if a[3] else 3 + a[9]) * a[19]),
 }
-ROOFLINE_BOUNDED = ("spc_group_points", "spc_three_interpolate", "spc_gather_points", "spc_sa_fused_forward")
+ROOFLINE_BOUNDED = ("spc_group_points", "spc_three_interpolate", "spc_gather_points", "spc_sa_fused_forward",
+                    "spc_sa_fused_forward_ex")
 
 
 class KernelMeter:
@@ -394,7 +400,7 @@ def run_ours(args):
         tensor_bound = avg_flops / (tf_peak * 1e12) > avg_bytes / (hbm_peak * 1e9)
         if tensor_bound:
             achieved = avg_flops / (avg_ms * 1e-3) / 1e12
-        roofline = {"kernel": name.replace("spc_", ""), "bound": "tensor" if tensor_bound else "hbm",
+        roofline = {"kernel": name.replace("spc_", "").replace("_ex", ""), "bound": "tensor" if tensor_bound else "hbm",
                     "achieved": round(achieved, 2),
                     "peak": tf_peak if tensor_bound else hbm_peak,
                     "unit": "TFLOP/s" if tensor_bound else "GB/s",

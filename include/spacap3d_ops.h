@@ -171,6 +171,15 @@ int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *
                          int Cf, float radius, const void *W1_bf16, const float *b1,
                          const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample,
                          int C1, int C2, int C3, float *out, void *out_pm_bf16, void *stream);
+/* Same, plus optional HOST copies of the folded layer-0 weights (W0_host (C1,3+Cf), b0_host (C1); host memory, read
+ * during the call; NULL = not available).  In the in-line form with C1*(4+Cf) <= 768 the kernel then takes them by
+ * value through its parameters (constant bank) instead of staging W0 in shared memory.  Results are the same up to
+ * fp32 summation order (the bias is the first addend instead of the last). */
+int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_t *idx, const void *G_bf16,
+                            const float *feat, const float *W0, const float *b0, const float *W0_host,
+                            const float *b0_host, int Cf, float radius, const void *W1_bf16, const float *b1,
+                            const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample, int C1,
+                            int C2, int C3, float *out, void *out_pm_bf16, void *stream);
 
 /* ---- point-major (BF16) eval path of the feature-propagation and voting stages ------------------
  * These have no C++ counterpart in the reference; each replaces a chain of small ATen launches. */

@@ -133,6 +133,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load split into issue and wait, so that the load of the next 32 columns is in flight while the current
+// ones are processed.  tcgen05.wait::ld covers every earlier load of the thread; the registers are passed through
+// the wait as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -194,7 +221,14 @@ struct SaFusedParams {
   __nv_bfloat16 *out_pm;  // optional (B,np,C3): the same result point-major in bf16 (next layer's GEMM input)
   int B, n, np, ns;
   int num_tiles;          // B*np*ns/128
+  // in-line form, optional: the folded layer-0 weights BY VALUE, [c][k] with k = K0 holding the bias.  Kernel
+  // parameters live in constant bank 0, so `fmaf(p.w0c[const], x, acc)` compiles to an FFMA with a c[0x0][..]
+  // operand: no shared-memory load, no scoreboard wait (the LDS.128 weight loads and the FMAs waiting for them
+  // were the largest producer stall in ncu after the gather fix).
+  int use_w0c;
+  float w0c[768];
 };
+constexpr int SA_W0C_MAX = 768;
 
 constexpr int SA_ROWS = 128;        // rows (centre,neighbour pairs) per tile
 constexpr int SA_MAX_K0 = 3 + 16;   // MODE_INLINE supports up to 16 raw feature channels
@@ -208,10 +242,9 @@ constexpr int SA_W0_STRIDE = 20;    // floats per channel row of the inline laye
 // (ncu: stall_long_sb on the subtraction was as large as the whole layer-0 math).  Tiles never straddle scenes
 // (npoint*nsample % 128 == 0 is checked at launch), so scene / centre follow from 32-bit arithmetic on the tile index.
 template <int NIN, int NS>
-__device__ __forceinline__ void sa_inline_issue(const SaFusedParams &p, int tile, int r, int i, int tiles_per_scene,
+__device__ __forceinline__ void sa_inline_issue(const SaFusedParams &p, int b, int tile_in_scene, int r, int i,
                                                 float (&raw)[NIN + 2]) {
-  const int b = tile / tiles_per_scene;
-  const int j = ((tile - b * tiles_per_scene) * SA_ROWS + r) / NS;
+  const int j = (tile_in_scene * SA_ROWS + r) / NS;
   const float *pp = p.xyz + ((size_t)b * p.n + i) * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
   raw[0] = __ldg(pp + 0); raw[1] = __ldg(pp + 1); raw[2] = __ldg(pp + 2);
@@ -249,6 +282,29 @@ __device__ __forceinline__ void sa_inline_compute(const float (&in)[NIN], int r,
       acc[2] = fmaf(wa.z, in[k], acc[2]); acc[3] = fmaf(wa.w, in[k], acc[3]);
       acc[4] = fmaf(wb.x, in[k], acc[4]); acc[5] = fmaf(wb.y, in[k], acc[5]);
       acc[6] = fmaf(wb.z, in[k], acc[6]); acc[7] = fmaf(wb.w, in[k], acc[7]);
+    }
+    uint4 o;
+    o.x = pack_relu_bf16x2(acc[0], acc[1]);
+    o.y = pack_relu_bf16x2(acc[2], acc[3]);
+    o.z = pack_relu_bf16x2(acc[4], acc[5]);
+    o.w = pack_relu_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = o;
+  }
+}
+
+// Same layer with the weights read from the kernel parameters (constant bank); KC0 = first 8-channel chunk.
+template <int C1, int NKC, int NIN, int KC0>
+__device__ __forceinline__ void sa_inline_compute_const(const SaFusedParams &p, const float (&in)[NIN], int r,
+                                                        uint8_t *sH1) {
+#pragma unroll
+  for (int kc = KC0; kc < KC0 + NKC; ++kc) {
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = p.w0c[(kc * 8 + c) * NIN + NIN - 1];                       // folded bias
+#pragma unroll
+      for (int k = 0; k < NIN - 1; ++k) a = fmaf(p.w0c[(kc * 8 + c) * NIN + k], in[k], a);
+      acc[c] = a;
     }
     uint4 o;
     o.x = pack_relu_bf16x2(acc[0], acc[1]);
@@ -484,7 +540,12 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         const int t0 = (int)blockIdx.x, dt = (int)gridDim.x;
         float raw_next[NIN + 2];
         int i1 = __ldg(p.idx + (long long)t0 * SA_ROWS + r);
-        sa_inline_issue<NIN, NS>(p, t0, r, i1, tiles_per_scene, raw_next);
+        // (scene, tile within the scene) of the tile whose loads are issued next, advanced without a division
+        int nb = t0 / tiles_per_scene, nts = t0 - nb * tiles_per_scene;
+        const int db = dt / tiles_per_scene, dts = dt - db * tiles_per_scene;
+        auto advance = [&]() { nb += db; nts += dts; if (nts >= tiles_per_scene) { nts -= tiles_per_scene; ++nb; } };
+        sa_inline_issue<NIN, NS>(p, nb, nts, r, i1, raw_next);
+        advance();
         i1 = nt > 1 ? __ldg(p.idx + (long long)(t0 + dt) * SA_ROWS + r) : 0;
         for (int k = 0; k < nt; ++k) {
           const int s = k & 1, n = k >> 1;
@@ -492,11 +553,17 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
           float in[NIN];
           sa_inline_finish<NIN>(raw_next, inv_r, in);
           if (k + 1 < nt) {
-            sa_inline_issue<NIN, NS>(p, tile + dt, r, i1, tiles_per_scene, raw_next);
+            sa_inline_issue<NIN, NS>(p, nb, nts, r, i1, raw_next);
+            advance();
             if (k + 2 < nt) i1 = __ldg(p.idx + (long long)(tile + 2 * dt) * SA_ROWS + r);
           }
           mbarrier_wait_relaxed(&h1_empty[s], (unsigned)(n & 1) ^ 1u);
-          sa_inline_compute<C1, NKC, NIN>(in, r, half * NKC, sH1 + s * L::H1_BYTES, sW0);
+          if (C1 * NIN <= SA_W0C_MAX && p.use_w0c) {
+            if (half == 0) sa_inline_compute_const<C1, NKC, NIN, 0>(p, in, r, sH1 + s * L::H1_BYTES);
+            else sa_inline_compute_const<C1, NKC, NIN, NKC>(p, in, r, sH1 + s * L::H1_BYTES);
+          } else {
+            sa_inline_compute<C1, NKC, NIN>(in, r, half * NKC, sH1 + s * L::H1_BYTES, sW0);
+          }
           fence_proxy_async_smem();
           mbarrier_arrive(&h1_full[s]);
         }
@@ -574,10 +641,17 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
       mbarrier_wait_relaxed(&h2_empty[s], (unsigned)(n & 1) ^ 1u);   // MMA2(k-2) has consumed H2[s]
       tc_fence_after();
       uint8_t *h2 = sH2 + s * L::H2_BYTES;
+      const uint32_t t1 = tmem_base + ((uint32_t)(q * 32) << 16) + s * C2;
+      uint32_t rr[2][32];
+      tmem_ld32_issue(t1, rr[0]);
+      tmem_ld32_wait(rr[0]);
 #pragma unroll
-      for (int col0 = 0; col0 < C2; col0 += 32) {
+      for (int ch = 0; ch < C2 / 32; ++ch) {
+        const int col0 = ch * 32;
+        if (ch + 1 < C2 / 32) tmem_ld32_issue(t1 + col0 + 32, rr[(ch + 1) & 1]);   // in flight during the packing
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + s * C2 + col0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[ch & 1][i]);
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           const float4 ba = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8);
@@ -589,6 +663,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
           o.w = pack_relu_bf16x2(v[c8 * 8 + 6] + bb.z, v[c8 * 8 + 7] + bb.w);
           *reinterpret_cast<uint4 *>(h2 + sw128_off(r, (col0 >> 3) + c8, SA_ROWS)) = o;
         }
+        if (ch + 1 < C2 / 32) tmem_ld32_wait(rr[(ch + 1) & 1]);
       }
       tc_fence_before();
       fence_proxy_async_smem();
@@ -613,10 +688,17 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         // optional point-major bf16 copy: lanes = consecutive channels => 64-byte coalesced stores
         __nv_bfloat16 *opm = p.out_pm ? p.out_pm + ((size_t)b * p.np + j0) * C3 + ch : nullptr;
         float m64 = -INFINITY;
+        const uint32_t t2 = tmem_base + ((uint32_t)(q * 32) << 16) + L::TMEM_D2 + st * SA_ROWS;
+        uint32_t rr[2][32];
+        tmem_ld32_issue(t2, rr[0]);
+        tmem_ld32_wait(rr[0]);
 #pragma unroll
-        for (int cb = 0; cb < SA_ROWS; cb += 32) {
+        for (int cbi = 0; cbi < SA_ROWS / 32; ++cbi) {
+          const int cb = cbi * 32;
+          if (cbi + 1 < SA_ROWS / 32) tmem_ld32_issue(t2 + cb + 32, rr[(cbi + 1) & 1]);
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + L::TMEM_D2 + st * SA_ROWS + cb, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[cbi & 1][i]);
           if (NS <= 32) {
 #pragma unroll
             for (int gI = 0; gI < 32 / NS; ++gI) {
@@ -637,6 +719,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
               m64 = -INFINITY;
             }
           }
+          if (cbi + 1 < SA_ROWS / 32) tmem_ld32_wait(rr[(cbi + 1) & 1]);
         }
         tc_fence_before();
         mbarrier_arrive(&d2_empty[st]);
@@ -691,6 +774,16 @@ extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, cons
                                     const float *b1, const void *W2_bf16, const float *b2, int B, int n,
                                     int npoint, int nsample, int C1, int C2, int C3, float *out,
                                     void *out_pm_bf16, void *stream_) {
+  return spc_sa_fused_forward_ex(xyz, new_xyz, idx, G_bf16, feat, W0, b0, nullptr, nullptr, Cf, radius, W1_bf16, b1,
+                                 W2_bf16, b2, B, n, npoint, nsample, C1, C2, C3, out, out_pm_bf16, stream_);
+}
+
+extern "C" int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_t *idx,
+                                       const void *G_bf16, const float *feat, const float *W0,
+                                       const float *b0, const float *W0_host, const float *b0_host, int Cf,
+                                       float radius, const void *W1_bf16, const float *b1, const void *W2_bf16,
+                                       const float *b2, int B, int n, int npoint, int nsample, int C1, int C2,
+                                       int C3, float *out, void *out_pm_bf16, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && n >= 1 && npoint >= 0 && nsample >= 1, "sa_fused: bad sizes");
   if (B == 0 || npoint == 0) return SPC_OK;
   SPC_CHECK_ARG(xyz && new_xyz && idx && W0 && b0 && W1_bf16 && b1 && W2_bf16 && b2 && out,
@@ -712,6 +805,15 @@ extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, cons
   p.W1 = (const __nv_bfloat16 *)W1_bf16; p.b1 = b1; p.W2 = (const __nv_bfloat16 *)W2_bf16; p.b2 = b2;
   p.out = out; p.out_pm = (__nv_bfloat16 *)out_pm_bf16; p.B = B; p.n = n; p.np = npoint; p.ns = nsample;
   p.num_tiles = (int)(rows / SA_ROWS);
+  p.use_w0c = 0;
+  if (!proj && W0_host && b0_host && C1 * (4 + Cf) <= SA_W0C_MAX) {
+    const int K0 = 3 + Cf, NIN = K0 + 1;
+    for (int c = 0; c < C1; ++c) {
+      for (int k = 0; k < K0; ++k) p.w0c[c * NIN + k] = W0_host[c * K0 + k];
+      p.w0c[c * NIN + K0] = b0_host[c];
+    }
+    p.use_w0c = 1;
+  }
   cudaStream_t stream = (cudaStream_t)stream_;
 #define SA_TRY(c1, c2, c3, ns)                                                                       \
   if (C1 == c1 && C2 == c2 && C3 == c3 && nsample == ns)                                             \

@@ -95,6 +95,16 @@ class _FoldedMLP:
         self.data = None
         self._w0f_t = None
         self._w0x = None
+        self._host0 = None
+
+    def host0(self, W0, b0):
+        """Host copies of the folded layer-0 weights (the fused kernel takes them by value through its
+        parameters when they are small).  One device->host copy per weight refresh, never inside a graph capture."""
+        if self._host0 is None:
+            if torch.cuda.is_current_stream_capturing():
+                return None, None
+            self._host0 = (W0.cpu().contiguous(), b0.cpu().contiguous())
+        return self._host0
 
     def w0f_t(self, W0):
         """(Cf, C1) bf16: feature columns of the folded conv0, transposed for the projection GEMM."""
@@ -114,7 +124,7 @@ class _FoldedMLP:
         if key != self.key:
             self.key = key
             self.data = None
-            self._w0f_t = self._w0x = None
+            self._w0f_t = self._w0x = self._host0 = None
             blocks = list(mlp.children())
             if len(blocks) == 3:
                 folded = [_fold_conv_bn(b) for b in blocks]
@@ -301,8 +311,9 @@ class PointnetSAModuleVotes(nn.Module):
         try:
             if Cf <= INLINE_MAX_FEATURES:
                 feat = None if features is None else features.contiguous()
+                W0h, b0h = cache.host0(W0, b0)
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, feat=feat,
-                                                    radius=radius, want_point_major=True)
+                                                    radius=radius, want_point_major=True, W0_host=W0h, b0_host=b0h)
             else:
                 # conv0 hoisted out of the grouping: ONE bf16 GEMM over the n points gives the
                 # per-point feature projection; the xyz columns stay in fp32 inside the kernel
