@@ -300,7 +300,8 @@ def run_ours(args):
     if args.mode == "graph":
         # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
         from spacap3d_b200.pipeline import GraphedDetector
-        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS)
+        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS,
+                                 fps_cull=int(os.environ.get("SPC_BENCH_FPS_CULL", "2")))
         # the knobs are baked into the captured graphs; eager passes stay on the single-call defaults
         _lib.call("spc_set_fps_cluster", 0)
         _lib.call("spc_set_fps_cull", 0)

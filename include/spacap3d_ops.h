@@ -63,6 +63,10 @@ int spc_set_fps_cluster(int cluster_ctas);
  * the rounds whose new centre provably cannot lower any of its points' min-distances (bounding-box
  * test, conservative in fp32).  Results are identical; a single call is ~15 % slower, several calls
  * in flight on different streams finish sooner (fewer instructions issued).  Default 0. */
+/* Modes: 1 = coordinates and min-distances in registers (two 256-thread CTAs per SM); 2 = coordinates in shared
+ * memory (three CTAs per SM; what the graph pipeline uses); 3 = "full-SM" CTAs of 768 threads in clusters of
+ * ceil(N/15360) (a 40 k-point scene holds exactly 3 SMs; measured 7 % slower than mode 2 in the 16-stream pipeline:
+ * 24 warps per reduction level make a round slower than three independent 8-warp CTAs). */
 int spc_set_fps_cull(int on);
 int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                    float *new_xyz, int hint_ordered, void *workspace,

@@ -914,8 +914,8 @@ extern "C" int spc_set_fps_cluster(int cluster_ctas) {
 // streams gains ~5 % overall.  spacap3d_b200/pipeline.py turns it on; SPC_FPS_CULL=0/1 overrides.
 static int g_fps_cull = 0;
 extern "C" int spc_set_fps_cull(int on) {
-  if (on != 0 && on != 1 && on != 2) {
-    set_error("spc_set_fps_cull: %d is not 0, 1 or 2", on);
+  if (on != 0 && on != 1 && on != 2 && on != 3) {
+    set_error("spc_set_fps_cull: %d is not 0, 1, 2 or 3", on);
     return SPC_ERR_INVALID_ARG;
   }
   g_fps_cull = on;
@@ -1018,8 +1018,15 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   // ---- Morton-sorted, culled kernel: needs the caller's workspace (perm) ----------------------------
   if (workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && N >= 8192 && npoint >= 64 &&
       B <= 65535 && C <= 8 && fps_cull_enabled()) {
-    const int need256 = (int)(((long long)N + (long long)C * 256 - 1) / ((long long)C * 256));
-    if (need256 <= 20 && N <= FMS_THREADS * FMS_ITEMS) {
+    // mode 3: "full-SM" CTAs -- 768 threads x 20 points, ~215 KB of shared memory, clusters of ceil(N / 15360).
+    // The same work as mode 2 (three 256-thread CTAs per SM) but packed by construction: a 40 k-point scene holds
+    // exactly 3 SMs.  The hardware spreads the 64 small CTAs of a mode-2 batch over up to 64 SMs, where each of them
+    // blocks kernels that need a whole SM (the fused SA kernel) for the 1.5 ms the sampler runs.
+    const int cull_mode = fps_cull_mode();
+    const int TH = cull_mode == 3 ? 768 : 256;
+    const int Cc = cull_mode == 3 ? (int)(((long long)N + 768LL * 20 - 1) / (768LL * 20)) : C;
+    const int need256 = (int)(((long long)N + (long long)Cc * TH - 1) / ((long long)Cc * TH));
+    if (need256 <= 20 && Cc <= 8 && N <= FMS_THREADS * FMS_ITEMS) {
       int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
       const size_t sort_smem = (size_t)FMS_BINS * sizeof(int);
       static bool sort_attr_set = false;
@@ -1030,7 +1037,15 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
       fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(xyz, N, perm);
       SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
       const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;
-      const bool xyz_smem = fps_cull_mode() == 2;
+      if (cull_mode == 3) {
+        switch (P256) {
+          case 8: return launch_fps_cull<8, 768, true>(p, perm, B, Cc, stream);
+          case 10: return launch_fps_cull<10, 768, true>(p, perm, B, Cc, stream);
+          case 16: return launch_fps_cull<16, 768, true>(p, perm, B, Cc, stream);
+          default: return launch_fps_cull<20, 768, true>(p, perm, B, Cc, stream);
+        }
+      }
+      const bool xyz_smem = cull_mode == 2;
       switch (P256) {
         case 8: return xyz_smem ? launch_fps_cull<8, 256, true>(p, perm, B, C, stream) : launch_fps_cull<8, 256, false>(p, perm, B, C, stream);
         case 10: return xyz_smem ? launch_fps_cull<10, 256, true>(p, perm, B, C, stream) : launch_fps_cull<10, 256, false>(p, perm, B, C, stream);

@@ -48,7 +48,7 @@ def test_fps_large_clouds(ext, name, monkeypatch):
     workspace, or culling off) and the oracle all agree bit for bit."""
     xyz, m = cases.fps_large_cases()[name]
     want = oracle.furthest_point_sampling(xyz, m)
-    for mode in ("1", "2"):       # coordinates in registers / in shared memory (three CTAs per SM)
+    for mode in ("1", "2", "3"):  # coordinates in registers / in shared memory (three CTAs per SM) / full-SM CTAs
         monkeypatch.setenv("SPC_FPS_CULL", mode)
         got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
         np.testing.assert_array_equal(got, want)
@@ -75,7 +75,7 @@ def test_fps_culled_every_cluster_size(ext, cluster, mode):
     np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_fps_strict_sequence_flags_and_chain(ext, mode):
     """spc_furthest_point_sampling_ex2: the culled kernels report per scene whether every pick was a strict
     unique maximum; the next samplers use that instead of the proof kernels.  Whatever the flags say, every
@@ -125,7 +125,7 @@ def test_fps_culled_scene_40k(ext):
     from spacap3d_b200 import _lib
     xyz, m = cases.fps_cases()["scene_40k"]
     want = oracle.furthest_point_sampling(xyz, m)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         _lib.call("spc_set_fps_cull", mode)
         try:
             got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
