@@ -268,6 +268,54 @@ def timed_loop(step_fn, steps, warmup, flush, barrier, sampler=None):
     return [a.elapsed_time(b) for a, b in ev], wall, clocks
 
 
+def hbm_bound_ops(pc, flush, hbm_peak):
+    """The HBM-bound point ops the north_star sets a roofline target for, timed live on BASELINE shapes (they are not
+    launched by the eval forward, where the fused SA kernel replaces grouping): grouping forward at config 4's SA1
+    shape (132 channels) and at SA2's, three_interpolate at FP2's.  CUDA events around 10 launches with an L2 flush
+    before each; algorithmic bytes = SURVEY 8(d) formulas."""
+    from spacap3d_b200 import _ext
+    xyz = pc[:, :, :3].contiguous()
+    B, N = xyz.shape[0], xyz.shape[1]
+    out = []
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    _, c1 = _ext.furthest_point_sampling_with_xyz(xyz, 2048)
+    _, c2 = _ext.furthest_point_sampling_with_xyz(c1, 1024)
+    for name, pts, ctr, r, ns, C in (("group_points SA1 multiview (config 4)", xyz, c1, 0.2, 64, 132),
+                                     ("group_points SA2", c1, c2, 0.4, 32, 128)):
+        n, npnt = pts.shape[1], ctr.shape[1]
+        idx = _ext.ball_query(ctr, pts, r, ns)
+        feats = torch.randn(B, C, n, device=pc.device)
+        ms = timed(lambda: _ext.group_points(feats, idx))
+        nbytes = 4 * B * (C * n + npnt * ns + C * npnt * ns)
+        out.append({"op": name, "shape": [B, C, n, npnt, ns], "ms": round(ms, 4), "algo_bytes": nbytes,
+                    "gbs": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / hbm_peak, 3)})
+        del feats
+    _, c3 = _ext.furthest_point_sampling_with_xyz(c2, 512)
+    d2, idx3 = _ext.three_nn(c2, c3)
+    w = torch.rand(B, 1024, 3, device=pc.device)
+    feats = torch.randn(B, 256, 512, device=pc.device)
+    ms = timed(lambda: _ext.three_interpolate(feats, idx3, w))
+    nbytes = 4 * B * (256 * 512 + 6 * 1024 + 256 * 1024)
+    out.append({"op": "three_interpolate FP2", "shape": [B, 256, 512, 1024], "ms": round(ms, 4), "algo_bytes": nbytes,
+                "gbs": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / hbm_peak, 3),
+                "note": "9.6 MB per call: launch-latency-bound, not bandwidth-bound"})
+    return out
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
@@ -456,6 +504,7 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline(model)
+    hbm_ops = hbm_bound_ops(resident[0], flush, hbm_peak) if rank == 0 and world == 1 else None
 
     if rank == 0:
         line = {
@@ -476,7 +525,7 @@ def run_ours(args):
                     "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roofline, "latency_bound": latency_bound, "ops": ops,
+            "roofline": roofline, "hbm_ops": hbm_ops, "latency_bound": latency_bound, "ops": ops,
             "kernel_ms_per_step": round(step_ms_kernels, 4),
             "eager": eager,
             "cpu_baseline": cpu_base, "clocks": clocks,
