@@ -359,7 +359,8 @@ def run_ours(args):
         # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
         from spacap3d_b200.pipeline import GraphedDetector
         runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS,
-                                 fps_cull=int(os.environ.get("SPC_BENCH_FPS_CULL", "2")))
+                                 fps_cull=int(os.environ.get("SPC_BENCH_FPS_CULL", "2")),
+                                 sa_min_tiles=int(os.environ.get("SPC_BENCH_SA_MIN_TILES", "16")))
         # the knobs are baked into the captured graphs; eager passes stay on the single-call defaults
         _lib.call("spc_set_fps_cluster", 0)
         _lib.call("spc_set_fps_cull", 0)

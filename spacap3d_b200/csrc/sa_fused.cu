@@ -133,33 +133,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// The same load split into issue and wait, so that the load of the next 32 columns is in flight while the current
-// ones are processed.  tcgen05.wait::ld covers every earlier load of the thread; the registers are passed through
-// the wait as in/out operands so that no use of them can be scheduled above it.
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
-                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
-                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
-                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-               :
-               : "memory");
-}
-
 // UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, both K-major
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -388,7 +361,7 @@ __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, 
 constexpr int SAP_PROD_WARPS = 8;
 constexpr int SAP_THREADS = 17 * 32;
 
-template <int C1, int C2, int C3>
+template <int C1, int C2, int C3, int OCC = 1>
 struct SaPipeSmem {
   static constexpr int W1_BYTES = C2 * C1 * 2;
   static constexpr int W2_BYTES = C3 * C2 * 2;
@@ -403,7 +376,10 @@ struct SaPipeSmem {
   static constexpr int TOTAL_PROJ = OFF_W0;
   static constexpr int TOTAL_INLINE = OFF_W0 + C1 * SA_W0_STRIDE * 4;
   static constexpr int TMEM_D2 = 2 * C2;                      // first column of the D2 ring
-  static constexpr int TMEM_COLS = 512;
+  // OCC = 2 (two CTAs per SM; only the narrow SA1 widths fit): a single D2 block, so that a CTA needs
+  // 2*C2 + 128 <= 256 of the SM's 512 TMEM columns; the other resident CTA covers the lost MMA2 / epilogue-2 overlap
+  static constexpr int D2_STAGES = OCC == 2 ? 1 : 2;
+  static constexpr int TMEM_COLS = OCC == 2 ? 256 : 512;
 };
 
 __device__ __forceinline__ void mbarrier_arrive(uint64_t *bar) {
@@ -433,9 +409,10 @@ __device__ __forceinline__ void sa_stage_weights(uint8_t *dst, const __nv_bfloat
   }
 }
 
-template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
-__global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaFusedParams p) {
-  using L = SaPipeSmem<C1, C2, C3>;
+template <int C1, int C2, int C3, int NS, bool MODE_PROJ, int OCC>
+__global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const SaFusedParams p) {
+  using L = SaPipeSmem<C1, C2, C3, OCC>;
+  constexpr int D2S = L::D2_STAGES;
   constexpr int NB = C3 / 128;                       // 128-channel output blocks per tile
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // the 128B-swizzle atoms must start on 1024-byte boundaries
@@ -574,19 +551,25 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         case 6: run(std::integral_constant<int, 6>{}); break;
         case 7: run(std::integral_constant<int, 7>{}); break;
         case 8: run(std::integral_constant<int, 8>{}); break;
-        case 9: run(std::integral_constant<int, 9>{}); break;
-        case 10: run(std::integral_constant<int, 10>{}); break;
-        case 11: run(std::integral_constant<int, 11>{}); break;
-        case 12: run(std::integral_constant<int, 12>{}); break;
-        case 13: run(std::integral_constant<int, 13>{}); break;
-        case 14: run(std::integral_constant<int, 14>{}); break;
-        case 15: run(std::integral_constant<int, 15>{}); break;
-        case 16: run(std::integral_constant<int, 16>{}); break;
-        case 17: run(std::integral_constant<int, 17>{}); break;
-        case 18: run(std::integral_constant<int, 18>{}); break;
-        case 19: run(std::integral_constant<int, 19>{}); break;
-        case 20: run(std::integral_constant<int, 20>{}); break;
-        default: break;
+        default:
+          if constexpr (OCC == 1) {                                // the two-CTA build (56 registers) only takes <= 4 raw channels
+            switch (K0 + 1) {
+              case 9: run(std::integral_constant<int, 9>{}); break;
+              case 10: run(std::integral_constant<int, 10>{}); break;
+              case 11: run(std::integral_constant<int, 11>{}); break;
+              case 12: run(std::integral_constant<int, 12>{}); break;
+              case 13: run(std::integral_constant<int, 13>{}); break;
+              case 14: run(std::integral_constant<int, 14>{}); break;
+              case 15: run(std::integral_constant<int, 15>{}); break;
+              case 16: run(std::integral_constant<int, 16>{}); break;
+              case 17: run(std::integral_constant<int, 17>{}); break;
+              case 18: run(std::integral_constant<int, 18>{}); break;
+              case 19: run(std::integral_constant<int, 19>{}); break;
+              case 20: run(std::integral_constant<int, 20>{}); break;
+              default: break;
+            }
+          }
+          break;
       }
     }
   } else if (warp == 16) {
@@ -616,7 +599,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
           tc_fence_after();
 #pragma unroll
           for (int h = 0; h < NB; ++h) {
-            const int u = kt * NB + h, st = u & 1, nu = u >> 1;
+            const int u = kt * NB + h, st = u % D2S, nu = u / D2S;
             mbarrier_wait(&d2_empty[st], (unsigned)(nu & 1) ^ 1u);
             tc_fence_after();
 #pragma unroll
@@ -641,17 +624,10 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
       mbarrier_wait_relaxed(&h2_empty[s], (unsigned)(n & 1) ^ 1u);   // MMA2(k-2) has consumed H2[s]
       tc_fence_after();
       uint8_t *h2 = sH2 + s * L::H2_BYTES;
-      const uint32_t t1 = tmem_base + ((uint32_t)(q * 32) << 16) + s * C2;
-      uint32_t rr[2][32];
-      tmem_ld32_issue(t1, rr[0]);
-      tmem_ld32_wait(rr[0]);
 #pragma unroll
-      for (int ch = 0; ch < C2 / 32; ++ch) {
-        const int col0 = ch * 32;
-        if (ch + 1 < C2 / 32) tmem_ld32_issue(t1 + col0 + 32, rr[(ch + 1) & 1]);   // in flight during the packing
+      for (int col0 = 0; col0 < C2; col0 += 32) {
         float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[ch & 1][i]);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + s * C2 + col0, v);
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
           const float4 ba = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8);
@@ -663,7 +639,6 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
           o.w = pack_relu_bf16x2(v[c8 * 8 + 6] + bb.z, v[c8 * 8 + 7] + bb.w);
           *reinterpret_cast<uint4 *>(h2 + sw128_off(r, (col0 >> 3) + c8, SA_ROWS)) = o;
         }
-        if (ch + 1 < C2 / 32) tmem_ld32_wait(rr[(ch + 1) & 1]);
       }
       tc_fence_before();
       fence_proxy_async_smem();
@@ -679,7 +654,7 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
       const int j0 = ((tile - b * tiles_per_scene) * SA_ROWS) / NS;      // first centre of the tile
 #pragma unroll
       for (int h = 0; h < NB; ++h) {
-        const int u = k * NB + h, st = u & 1, nu = u >> 1;
+        const int u = k * NB + h, st = u % D2S, nu = u / D2S;
         mbarrier_wait_relaxed(&d2_full[st], (unsigned)(nu & 1));
         tc_fence_after();
         const int ch = h * 128 + q * 32 + lane;
@@ -688,17 +663,10 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
         // optional point-major bf16 copy: lanes = consecutive channels => 64-byte coalesced stores
         __nv_bfloat16 *opm = p.out_pm ? p.out_pm + ((size_t)b * p.np + j0) * C3 + ch : nullptr;
         float m64 = -INFINITY;
-        const uint32_t t2 = tmem_base + ((uint32_t)(q * 32) << 16) + L::TMEM_D2 + st * SA_ROWS;
-        uint32_t rr[2][32];
-        tmem_ld32_issue(t2, rr[0]);
-        tmem_ld32_wait(rr[0]);
 #pragma unroll
-        for (int cbi = 0; cbi < SA_ROWS / 32; ++cbi) {
-          const int cb = cbi * 32;
-          if (cbi + 1 < SA_ROWS / 32) tmem_ld32_issue(t2 + cb + 32, rr[(cbi + 1) & 1]);
+        for (int cb = 0; cb < SA_ROWS; cb += 32) {
           float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[cbi & 1][i]);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + L::TMEM_D2 + st * SA_ROWS + cb, v);
           if (NS <= 32) {
 #pragma unroll
             for (int gI = 0; gI < 32 / NS; ++gI) {
@@ -719,7 +687,6 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
               m64 = -INFINITY;
             }
           }
-          if (cbi + 1 < SA_ROWS / 32) tmem_ld32_wait(rr[(cbi + 1) & 1]);
         }
         tc_fence_before();
         mbarrier_arrive(&d2_empty[st]);
@@ -736,13 +703,13 @@ __global__ void __launch_bounds__(SAP_THREADS, 1) sa_fused_pipe_kernel(const SaF
 
 static int g_sa_min_tiles = 0;
 
-template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
-static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
-  using L = SaPipeSmem<C1, C2, C3>;
-  auto kern = sa_fused_pipe_kernel<C1, C2, C3, NS, MODE_PROJ>;
+template <int C1, int C2, int C3, int NS, bool MODE_PROJ, int OCC>
+static int launch_sa_pipe_occ(const SaFusedParams &p, cudaStream_t stream) {
+  using L = SaPipeSmem<C1, C2, C3, OCC>;
+  auto kern = sa_fused_pipe_kernel<C1, C2, C3, NS, MODE_PROJ, OCC>;
   const int smem = (MODE_PROJ ? L::TOTAL_PROJ : L::TOTAL_INLINE) + 1024;   // + slack for 1024-byte alignment
   SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  int grid = kNumSMs;
+  int grid = kNumSMs * OCC;
   if (grid > p.num_tiles) grid = p.num_tiles;
   // Throughput knob: every CTA pays a fixed cost (weight staging, TMEM allocation, pipeline fill); with few
   // tiles per CTA that cost dominates and a smaller grid spends less SM-time for the same work (slower alone,
@@ -753,6 +720,18 @@ static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   kern<<<grid, SAP_THREADS, smem, stream>>>(p);
   SPC_LAUNCH_CHECK("sa_fused_pipe_kernel");
   return SPC_OK;
+}
+
+// The narrow in-line configuration (SA1: 64,64,128) needs 94 KB of shared memory and 256 TMEM columns, so two CTAs
+// share an SM when the registers allow it (<= 56 per thread): 34 resident warps instead of 17 hide the latencies
+// that keep the single CTA at ~45 % issue utilisation.  SPC_SA_OCC=1 restores one CTA per SM for A/B runs.
+template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
+static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
+  if constexpr (!MODE_PROJ && 2 * C2 + 128 <= 256 && 2 * (SaPipeSmem<C1, C2, C3, 2>::TOTAL_INLINE + 1024) <= 227 * 1024) {
+    static const bool occ2 = []() { const char *e = getenv("SPC_SA_OCC"); return !(e && atoi(e) == 1); }();
+    if (occ2 && p.Cf <= 4) return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 2>(p, stream);
+  }
+  return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 1>(p, stream);
 }
 
 }  // namespace spc
