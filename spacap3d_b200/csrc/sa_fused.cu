@@ -551,13 +551,13 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
         case 6: run(std::integral_constant<int, 6>{}); break;
         case 7: run(std::integral_constant<int, 7>{}); break;
         case 8: run(std::integral_constant<int, 8>{}); break;
+        case 9: run(std::integral_constant<int, 9>{}); break;
+        case 10: run(std::integral_constant<int, 10>{}); break;
+        case 11: run(std::integral_constant<int, 11>{}); break;
+        case 12: run(std::integral_constant<int, 12>{}); break;
         default:
-          if constexpr (OCC == 1) {                                // the two-CTA build (56 registers) only takes <= 4 raw channels
+          if constexpr (OCC == 1) {                                // the two-CTA build (56 registers) only takes <= 8 raw channels
             switch (K0 + 1) {
-              case 9: run(std::integral_constant<int, 9>{}); break;
-              case 10: run(std::integral_constant<int, 10>{}); break;
-              case 11: run(std::integral_constant<int, 11>{}); break;
-              case 12: run(std::integral_constant<int, 12>{}); break;
               case 13: run(std::integral_constant<int, 13>{}); break;
               case 14: run(std::integral_constant<int, 14>{}); break;
               case 15: run(std::integral_constant<int, 15>{}); break;
@@ -729,7 +729,7 @@ template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
 static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   if constexpr (!MODE_PROJ && 2 * C2 + 128 <= 256 && 2 * (SaPipeSmem<C1, C2, C3, 2>::TOTAL_INLINE + 1024) <= 227 * 1024) {
     static const bool occ2 = []() { const char *e = getenv("SPC_SA_OCC"); return !(e && atoi(e) == 1); }();
-    if (occ2 && p.Cf <= 4) return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 2>(p, stream);
+    if (occ2 && p.Cf <= 8) return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 2>(p, stream);
   }
   return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 1>(p, stream);
 }
