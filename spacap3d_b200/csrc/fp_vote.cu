@@ -15,8 +15,9 @@ namespace spc {
 //   norm = sum(dist_recip, dim=2);          weight = dist_recip / norm
 // Same arithmetic (IEEE sqrt / div, left-to-right sum); idx is bit-identical to three_nn.
 // ------------------------------------------------------------------------------------------------
-constexpr int NW_THREADS = 128;
-constexpr int NW_SPLIT = 4;          // lanes cooperating on one unknown point
+constexpr int NW_THREADS = 256;
+constexpr int NW_SPLIT = 8;          // lanes cooperating on one unknown point (power of two <= 32)
+constexpr int NW_SPLIT_LOG2 = 3;
 constexpr int NW_TILE = 1024;
 
 // insert candidate (d,i) into the ascending triple, ordering by (distance, index): the reference's
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const floa
   __shared__ float sx[NW_TILE], sy[NW_TILE], sz[NW_TILE];
   const int b = blockIdx.y;
   const int sub = threadIdx.x & (NW_SPLIT - 1);
-  const int j = blockIdx.x * (NW_THREADS / NW_SPLIT) + (threadIdx.x >> 2);
+  const int j = blockIdx.x * (NW_THREADS / NW_SPLIT) + (threadIdx.x >> NW_SPLIT_LOG2);
   const float *U = unknown + (size_t)b * n * 3;
   const float *K = known + (size_t)b * m * 3;
   const bool ok = j < n;
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const floa
       (comp == 0 ? sx : comp == 1 ? sy : sz)[pt] = v;
     }
     __syncthreads();
-    for (int k = sub; k < tile; k += NW_SPLIT) {       // each lane of the quad scans every 4th point
+    for (int k = sub; k < tile; k += NW_SPLIT) {       // each lane of the group scans every NW_SPLIT-th point
       const float d = sqdist_ref(ux, uy, uz, sx[k], sy[k], sz[k]);
       if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = base + k; }
       else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = base + k; }

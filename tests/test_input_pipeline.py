@@ -166,3 +166,26 @@ def test_store_rejects_missing_multiview():
     st.multiview = None
     with pytest.raises(RuntimeError, match="multiview"):
         st.make_batch([], [], use_multiview=True)
+
+
+@pytest.mark.gpu
+def test_store_feeds_detector():
+    """Row N4 -> the hot path: a batch assembled on the device goes straight into the detector (same layout as the
+    reference's data_dict['point_clouds']); the device sampler and the numpy-stream sampler both work."""
+    from spacap3d_b200.detector import VoteNetDetector
+    st = ip.DeviceSceneStore("cuda")
+    for i in range(2):
+        v, inst, sem, bb, _ = cases_input.make_scene(24000, 30, 300 + i)
+        st.add_scene("s%d" % i, v, inst, sem, bb)
+    st.finalize()
+    torch.manual_seed(0)
+    model = VoteNetDetector(input_feature_dim=1).cuda().eval()
+    draws = [ip.draw_item(np.random.RandomState(s), 24000, 20000, True) for s in range(2)]
+    dev_choices = ip.draw_batch_device([24000, 24000], 20000, generator=torch.Generator("cuda").manual_seed(3))
+    for d in (draws, (dev_choices, np.stack([x[1] for x in draws]))):
+        batch = st.make_batch(["s0", "s1"], d, use_height=True)
+        assert batch["point_clouds"].shape == (2, 20000, 4)
+        with torch.no_grad():
+            out = model({"point_clouds": batch["point_clouds"]})
+        assert out["bbox_corner"].shape == (2, 256, 8, 3) and torch.isfinite(out["center"]).all()
+        assert batch["vote_label"].shape == (2, 20000, 9) and batch["vote_label_mask"].sum() > 0
