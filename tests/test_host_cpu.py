@@ -133,3 +133,23 @@ def test_detector_end_to_end_on_cpu_oracle_provider():
               "aggregated_vote_inds", "objectness_scores", "center", "heading_scores",
               "heading_residuals", "size_scores", "bbox_mask", "bbox_sems", "sem_cls", "bbox_feature"):
         assert k in out, k
+
+
+def test_bench_byte_and_flop_models_match_the_abi():
+    """bench.py models algorithmic bytes / flops from the ctypes argument lists: every modelled entry point must
+    exist in the ABI table and the model must not index past its arguments (an ABI change once silently dropped
+    the fused-SA kernel from the roofline)."""
+    import bench
+    from spacap3d_b200 import _lib
+    for table in (bench.ALGO_BYTES, bench.ALGO_FLOPS):
+        for name, fn in table.items():
+            assert name in _lib.SIGNATURES, name
+            args = [1] * len(_lib.SIGNATURES[name])
+            assert fn(args) >= 0
+    for name in bench.ROOFLINE_BOUNDED:
+        assert name in _lib.SIGNATURES, name
+    # the fused-SA models of the two entry points agree on the same call
+    a = [0, 0, 0, 0, 0, 0, 0, 1, 0.2, 0, 0, 0, 0, 8, 40000, 2048, 64, 64, 64, 128, 0, 0, 0]
+    a_ex = a[:7] + [0, 0] + a[7:]
+    assert bench.ALGO_BYTES["spc_sa_fused_forward"](a) == bench.ALGO_BYTES["spc_sa_fused_forward_ex"](a_ex)
+    assert bench.ALGO_FLOPS["spc_sa_fused_forward"](a) == bench.ALGO_FLOPS["spc_sa_fused_forward_ex"](a_ex)
