@@ -410,6 +410,151 @@ __global__ void __launch_bounds__(GG_FILL_WARPS * 32) gg_fill_kernel(const int32
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// One-kernel list build (N <= 8192): histogram + scan + a TWO-LEVEL stable counting sort, one CTA per
+// (scene, partition).  The fill above lets every warp (32 points) scan all Sp positions -- N/32 x Sp/32
+// warp iterations, 43 us at the SA2 shape and a third of the whole backward.  Here
+//   A. the positions are first bucketed by key >> 5 (<= 256 buckets): warp w walks its contiguous chunk of
+//      positions, counts per bucket (match.any, no atomics: a row of counters per warp), the counters are
+//      turned into start offsets (bucket b starts where the list of key 32b starts, then warp by warp), and
+//      a second walk in the same order scatters the positions => stable;
+//   B. one warp per bucket orders its (short) region by the low 5 key bits with per-key cursors, again in
+//      position order => every list ascending, exactly what gg_fill_kernel produces (tested bit for bit).
+// Work: 2 x Sp/32 + Sp/32 + N/32 warp iterations per partition instead of N/32 x Sp/32.
+// ----------------------------------------------------------------------------------------------
+constexpr int GB_THREADS = 1024;
+constexpr int GB_MAX_N = 8192;
+
+static size_t gg_build_smem(int N, int Sp, int Np) {
+  const int nbk = (N + 31) >> 5;
+  return (size_t)Sp * sizeof(int) + (size_t)Np * sizeof(int) + (size_t)32 * nbk * sizeof(int) +
+         (size_t)Sp * sizeof(uint16_t) + 16;
+}
+
+__global__ void __launch_bounds__(GB_THREADS) gg_build_kernel(const int32_t *__restrict__ idx, int N, int S, int Sp,
+                                                              int H, int Np, int *__restrict__ offsets,
+                                                              uint16_t *__restrict__ order) {
+  extern __shared__ __align__(128) int gb_smem[];
+  __shared__ int s_part[32];
+  __shared__ int s_cur[32][32];
+  __shared__ __align__(8) uint64_t bar;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p0 = h * Sp, len = min(S, p0 + Sp) - p0;
+  const int NBK = (N + 31) >> 5;
+  int *s_idx = gb_smem;                 // [Sp]
+  int *s_off = s_idx + Sp;              // [Np]  histogram, then exclusive offsets (slot i = start of list i)
+  int *s_cnt = s_off + Np;              // [32 warps][NBK]
+  uint16_t *s_bk = reinterpret_cast<uint16_t *>(s_cnt + 32 * NBK);   // [Sp] positions grouped by bucket
+  const int32_t *ix = idx + (size_t)b * S + p0;
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(ix) & 15) == 0) && (len % 4 == 0);
+  if (bulk_ok) {
+    if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&bar, (unsigned)(len * sizeof(int)));
+      bulk_g2s(s_idx, ix, (unsigned)(len * sizeof(int)), &bar);
+    }
+  } else {
+    for (int e = tid; e < len; e += GB_THREADS) s_idx[e] = __ldg(ix + e);
+  }
+  for (int e = tid; e < Np; e += GB_THREADS) s_off[e] = 0;
+  for (int e = tid; e < 32 * NBK; e += GB_THREADS) s_cnt[e] = 0;
+  if (bulk_ok) mbar_wait(&bar, 0);
+  __syncthreads();
+  // ---- histogram and scan: s_off[i] = number of positions with key < i ---------------------------------
+  for (int t = tid; t < len; t += GB_THREADS) {
+    const int k = s_idx[t];
+    if ((unsigned)k < (unsigned)N) atomicAdd(&s_off[1 + k], 1);
+  }
+  __syncthreads();
+  {
+    int *row = s_off + 1;
+    const int per = (N + GB_THREADS - 1) / GB_THREADS;
+    const int e0 = min(N, tid * per), e1 = min(N, e0 + per);
+    int sum = 0;
+    for (int e = e0; e < e1; ++e) sum += row[e];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_part[lane];
+      int inc2 = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += u; }
+      s_part[lane] = inc2 - v;
+    }
+    __syncthreads();
+    int run = s_part[warp] + incl - sum;
+    for (int e = e0; e < e1; ++e) { run += row[e]; row[e] = run; }
+  }
+  __syncthreads();
+  int *off_g = offsets + ((size_t)b * H + h) * Np;
+  for (int e = tid; e < Np; e += GB_THREADS) off_g[e] = e <= N ? s_off[e] : 0;
+  // ---- A: stable bucketing by key >> 5 ---------------------------------------------------------------
+  const int CH = (((len + 31) / 32 + 31) / 32) * 32;     // positions per warp, a multiple of 32
+  const int c0 = min(len, warp * CH), c1 = min(len, c0 + CH);
+  int *cw = s_cnt + warp * NBK;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int t0 = c0; t0 < c1; t0 += 32) {
+    const int t = t0 + lane;
+    const int k = t < c1 ? s_idx[t] : -1;
+    const bool valid = (unsigned)k < (unsigned)N;
+    const int bkt = k >> 5;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? bkt : NBK + lane);
+    if (valid && (peers & lt) == 0u) cw[bkt] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int bk = tid; bk < NBK; bk += GB_THREADS) {
+    int run = s_off[32 * bk];
+    for (int w = 0; w < 32; ++w) { const int c = s_cnt[w * NBK + bk]; s_cnt[w * NBK + bk] = run; run += c; }
+  }
+  __syncthreads();
+  for (int t0 = c0; t0 < c1; t0 += 32) {
+    const int t = t0 + lane;
+    const int k = t < c1 ? s_idx[t] : -1;
+    const bool valid = (unsigned)k < (unsigned)N;
+    const int bkt = k >> 5;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? bkt : NBK + lane);
+    const int base = valid ? cw[bkt] : 0;
+    __syncwarp();
+    if (valid) {
+      const unsigned before = peers & lt;
+      s_bk[base + __popc(before)] = (uint16_t)t;
+      if (before == 0u) cw[bkt] = base + __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- B: one warp per bucket, stable by the low five key bits ----------------------------------------
+  uint16_t *ord = order + (size_t)b * S + p0;
+  for (int bk = warp; bk < NBK; bk += 32) {
+    const int k0 = 32 * bk;
+    const int r0 = s_off[k0], r1 = s_off[min(N, k0 + 32)];
+    s_cur[warp][lane] = (k0 + lane < N) ? s_off[k0 + lane] : 0;
+    __syncwarp();
+    for (int e0 = r0; e0 < r1; e0 += 32) {
+      const int e = e0 + lane;
+      const bool valid = e < r1;
+      const int pos = valid ? (int)s_bk[e] : 0;
+      const int kl = valid ? (s_idx[pos] & 31) : 0;
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? kl : 32 + lane);
+      const int base = valid ? s_cur[warp][kl] : 0;
+      __syncwarp();
+      if (valid) {
+        const unsigned before = peers & lt;
+        ord[base + __popc(before)] = (uint16_t)pos;
+        if (before == 0u) s_cur[warp][kl] = base + __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+  }
+}
+
 template <int CT, bool LISTS_SMEM>
 __global__ void __launch_bounds__(GG_THREADS) group_points_grad_csr_kernel(
     const float *__restrict__ grad_out, const int *__restrict__ offsets, const uint16_t *__restrict__ order,
@@ -659,13 +804,20 @@ extern "C" int spc_group_points_grad_ex(const float *grad_out, const int32_t *id
   int *offsets = reinterpret_cast<int *>(workspace);
   const size_t off_bytes = (size_t)B * g.H * (size_t)g.Np * sizeof(int);
   uint16_t *order = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(workspace) + off_bytes);
-  SPC_CUDA(cudaMemsetAsync(offsets, 0, off_bytes, stream));
-  gg_hist_kernel<<<dim3(ceil_div(S, 256), B), 256, 0, stream>>>(idx, N, S, g.Sp, g.H, g.Np, offsets);
-  gg_scan_kernel<<<B * g.H, 1024, 0, stream>>>(N, g.Np, offsets);
-  const size_t fill_smem = (size_t)g.Sp * sizeof(int);
-  SPC_CUDA(cudaFuncSetAttribute(gg_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-  gg_fill_kernel<<<dim3(ceil_div(N, 32 * GG_FILL_WARPS), g.H, B), GG_FILL_WARPS * 32, fill_smem, stream>>>(
-      idx, N, S, g.Sp, g.H, g.Np, offsets, order);
+  const size_t build_smem = gg_build_smem(N, g.Sp, g.Np);
+  if (N <= GB_MAX_N && build_smem <= 220 * 1024 && !getenv("SPC_GROUP_GRAD_OLD_FILL")) {
+    // histogram + scan + two-level stable sort in one kernel per (scene, partition)
+    SPC_CUDA(cudaFuncSetAttribute(gg_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem));
+    gg_build_kernel<<<dim3(g.H, B), GB_THREADS, build_smem, stream>>>(idx, N, S, g.Sp, g.H, g.Np, offsets, order);
+  } else {
+    SPC_CUDA(cudaMemsetAsync(offsets, 0, off_bytes, stream));
+    gg_hist_kernel<<<dim3(ceil_div(S, 256), B), 256, 0, stream>>>(idx, N, S, g.Sp, g.H, g.Np, offsets);
+    gg_scan_kernel<<<B * g.H, 1024, 0, stream>>>(N, g.Np, offsets);
+    const size_t fill_smem = (size_t)g.Sp * sizeof(int);
+    SPC_CUDA(cudaFuncSetAttribute(gg_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    gg_fill_kernel<<<dim3(ceil_div(N, 32 * GG_FILL_WARPS), g.H, B), GG_FILL_WARPS * 32, fill_smem, stream>>>(
+        idx, N, S, g.Sp, g.H, g.Np, offsets, order);
+  }
   SPC_LAUNCH_CHECK("group_points_grad list build");
   if (g.H > 1) SPC_CUDA(cudaMemsetAsync(grad_points, 0, (size_t)B * C * N * sizeof(float), stream));
 #define GG_CASE(ct)                                                                                              \

@@ -220,6 +220,12 @@ def test_group_grad_list_based(ext, ref_ext, name, monkeypatch):
     if npoint * ns <= 49152:
         for _ in range(3):
             np.testing.assert_array_equal(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), got)
+    if npoint * ns <= 49152:
+        # the one-kernel list build (two-level stable sort) and the original per-warp scan produce the same
+        # ascending lists, hence bit-identical sums
+        monkeypatch.setenv("SPC_GROUP_GRAD_OLD_FILL", "1")
+        np.testing.assert_array_equal(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), got)
+        monkeypatch.delenv("SPC_GROUP_GRAD_OLD_FILL")
     monkeypatch.setenv("SPC_GROUP_GRAD_ATOMIC", "1")
     np.testing.assert_allclose(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), want, **tol)
     if ref_ext is not None:
