@@ -153,3 +153,19 @@ def test_bench_byte_and_flop_models_match_the_abi():
     a_ex = a[:7] + [0, 0] + a[7:]
     assert bench.ALGO_BYTES["spc_sa_fused_forward"](a) == bench.ALGO_BYTES["spc_sa_fused_forward_ex"](a_ex)
     assert bench.ALGO_FLOPS["spc_sa_fused_forward"](a) == bench.ALGO_FLOPS["spc_sa_fused_forward_ex"](a_ex)
+
+
+def test_bench_reference_arm_runs_without_a_gpu():
+    """`bench.py --impl reference` must always print one JSON line: here (no GPU, hence no reference CUDA extension)
+    it times the CPU oracle port on a bounded sample; the keys the driver reads are all present."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "detector scenes/s @40k pts" and line["value"] > 0
+    assert line["unit"] == "scenes/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 0
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert "workload" in line["config"] and "model" not in line["config"]
