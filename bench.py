@@ -626,7 +626,7 @@ def reference_host_decode(self, data_dict):
     return torch.cat(boxes, 0)
 
 
-def cpu_baseline(model_gpu, budget_s=20.0):
+def cpu_baseline(model_gpu, budget_s=12.0):
     """BASELINE.json configs[0]: one 40k-point scene, batch 1, full detector forward with the CPU
     oracle ops (C port of the reference kernels, OpenMP) + torch CPU MLPs, on the host cores."""
     import copy
@@ -643,7 +643,7 @@ def cpu_baseline(model_gpu, budget_s=20.0):
             model({"point_clouds": scenes[n % 2]})
             n += 1
             el = time.perf_counter() - t0
-            if el > budget_s or n >= 12:
+            if el > budget_s or n >= 200:        # a bounded sample of ~12 s of CPU work
                 break
     return {"value": round(n / el, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
             "sample": "%d forward(s) of one 40k-pt scene, batch 1 (configs[0]), %.1f s; oracle C ops "
