@@ -25,6 +25,12 @@
 //   out[b, c, j] = relu(max_k D2[c, j*ns+k] + b2[c])   (ReLU and +b commute with max)
 // BN (eval) is folded on the host: W' = diag(gamma/sqrt(var+eps)) W, b = beta - mean*scale.
 //
+// Execution: a persistent grid of warp-specialised CTAs (8 producer warps, 4 + 4 epilogue warps, 1 MMA-issuing
+// warp, mbarrier hand-offs, H1 / H2 / D1 double-buffered).  The narrow in-line configuration (SA1: 94 KB of shared
+// memory, one D2 block => 256 TMEM columns, 56 registers) runs TWO CTAs per SM; the wide ones (up to 224 KB) one.
+// The in-line layer-0 weights reach the kernel by value in its parameters (constant bank -> uniform registers) when
+// the caller supplies host copies (spc_sa_fused_forward_ex), else they are staged in shared memory.
+//
 // Shared-memory operands: canonical UMMA K-major layout with 128-byte swizzle (a row = 128
 // contiguous bytes per 64-element K atom, chunk c of row r at position c ^ (r & 7)).  With it both
 // a warp writing one whole row (row-wise gather) and 8 lanes writing the same chunk of 8
