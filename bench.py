@@ -1,25 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- detector scenes/s @40k points on N B200s (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one full detector forward (PointNet++ backbone SA1-4 + FP1-2, Hough voting, vote
-aggregation + proposal head + on-device box decode) over one batch of 8 synthetic 40k-point
-ScanNet-shaped scenes per GPU (BASELINE.json configs[1]; weak scaling: every rank has its own 8
-scenes, no data-path collective -- inference is embarrassingly parallel over scenes).
+aggregation + proposal head + on-device box decode) over one batch of synthetic 40k-point
+ScanNet-shaped scenes per GPU.  --config selects the BASELINE.json workload:
+  2 (default, the config the metric is quoted on)  xyz+height, 8 scenes per GPU, weak scaling
+  3  xyz+rgb+normal+height (C=7), 32 scenes in total sharded over the ranks (strong scaling); detector
+     only -- the captioner is a non-target PyTorch path
+  4  xyz+multiview+normal+height (C=132), 8 scenes per GPU (64 on 8 GPUs), weak scaling
+  5  training sweep: forward + backward + one NCCL gradient all-reduce, 4 scenes per GPU,
+     --points N (40k..200k) with the SA npoint scaled by N/40k
+Inference is embarrassingly parallel over scenes: no data-path collective.
 
-  value   : scenes/s with the batch already resident in HBM (CUDA-event time, max over ranks)
-  e2e     : same, through the public module API from PINNED HOST buffers, host->device copy and
+  value   : scenes/s with the batch already resident in HBM (CUDA-event time, max over ranks); the
+            K-step timed region is repeated REPEATS times and the MEDIAN region is reported
+  e2e     : same, through the public API from PINNED HOST buffers, host->device copy and
             device->host read of the detections inside the timed region
   roofline: the dominant roofline-bounded kernel of the step, timed live with CUDA events
+  dominant: the kernel with the largest share of the step's time, whatever bounds it
   cpu_baseline: the CPU oracle port (oracle/, C + torch CPU MLP) on a bounded sample (rank 0, N=1)
-  --impl reference: the reference's own CUDA ops (oracle/_ref, unmodified sources rebuilt for
-            sm_100a) in the reference's own op sequence, incl. its host-side box decode; falls
-            back to the CPU port when oracle/_ref is not loadable.
+  --impl reference: the reference's UNMODIFIED Python stack (baseline/_ref: lib/pointnet2/*.py, models/*.py,
+            SpaCapNet detection branch incl. its host-side box decode) on the reference's own CUDA ops
+            (oracle/_ref, unmodified sources rebuilt for sm_100a), one replica per rank; falls back to the CPU
+            port when they are not loadable.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -34,14 +44,44 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENES_PER_GPU = 8
 N_POINTS = 40000
-FEATURE_DIM = 1          # xyz + height: the reference's default "xyz" input
-CONFIG_ID = 2
-WORKLOAD = ("SpaCap3D xyz: batch 8 scenes x 40k pts per GPU, full detector forward "
-            "(SA 2048/1024/512/256, FP1-2, voting, 256 proposals, box decode)")
-N_INPUT_SETS = 26        # distinct batches rotated through the timed loops: 26 x 5.12 MB = 133 MB > 126 MB L2
+REPEATS = 15             # the K-step timed region is repeated this often; the median region is reported
 N_STREAMS = 16           # CUDA-graph replay streams (batches are independent; FPS uses 64 of 148 SMs)
+L2_BYTES = 126e6
+
+CONFIGS = {
+    2: dict(feature_dim=1, scene_kw=dict(use_height=True), scenes_per_gpu=8, scenes_total=None, scaling="weak",
+            workload="SpaCap3D xyz: batch 8 scenes x 40k pts per GPU, full detector forward "
+                     "(SA 2048/1024/512/256, FP1-2, voting, 256 proposals, box decode)"),
+    3: dict(feature_dim=7, scene_kw=dict(use_color=True, use_normal=True, use_height=True), scenes_per_gpu=None,
+            scenes_total=32, scaling="strong",
+            workload="SpaCap3D xyz+rgb+normal: 32 scenes x 40k pts in total, 7 feature channels, sharded over the "
+                     "ranks, full detector forward (captioner = non-target PyTorch path, not run)"),
+    4: dict(feature_dim=132, scene_kw=dict(use_multiview=True, use_normal=True, use_height=True), scenes_per_gpu=8,
+            scenes_total=None, scaling="weak",
+            workload="SpaCap3D xyz+multiview+normal: batch 8 scenes x 40k pts per GPU (64 on 8 GPUs), 132 feature "
+                     "channels (128-d multiview), full detector forward"),
+    5: dict(feature_dim=1, scene_kw=dict(use_height=True), scenes_per_gpu=4, scenes_total=None, scaling="weak",
+            workload="SpaCap3D training sweep: 4 scenes per GPU, forward + backward + NCCL gradient all-reduce, "
+                     "SA npoint scaled with the cloud size"),
+}
+CFG = dict(CONFIGS[2], id=2)
+
+
+def scenes_per_gpu(world):
+    return CFG["scenes_per_gpu"] or max(1, CFG["scenes_total"] // world)
+
+
+def n_input_sets(world):
+    """Distinct batches rotated through the timed loops so that their total size exceeds the L2."""
+    batch_bytes = scenes_per_gpu(world) * N_POINTS * (3 + CFG["feature_dim"]) * 4
+    return max(3, int(math.ceil(1.06 * L2_BYTES / batch_bytes)))
+
+
+def workload_config(world):
+    """The part of `config` both arms print identically."""
+    return {"workload": CFG["workload"], "baseline_config": CFG["id"], "scenes_per_gpu": scenes_per_gpu(world),
+            "points": N_POINTS, "input_feature_dim": CFG["feature_dim"], "weights": weights_note()}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -60,15 +100,23 @@ def peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(tag):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu capture of this round (bench.py cannot run under a profiler); None when the file is missing."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_%s_traffic.json" % tag)
+def ncu_traffic(tag, source):
+    """(dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, where it comes from), from
+    this round's committed ncu capture (bench.py cannot run under a profiler).  The capture records the sha256 of the
+    kernel source it was taken from; when csrc/<source> has changed since, the figure is stale and None is reported."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "r2_%s_traffic.json" % tag)
     try:
         with open(path) as f:
-            return int(json.load(f)["dram_bytes_per_launch_avg"])
+            d = json.load(f)
+        with open(os.path.join(ROOT, "spacap3d_b200", "csrc", source), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        if d.get("source_sha256") != sha:
+            return None, "profiles/r2_%s_traffic.json is stale (csrc/%s changed since the capture)" % (tag, source)
+        return int(d["dram_bytes_per_launch_avg"]), ("profiles/r2_%s_traffic.json (ncu --set full, dram read+write per "
+                                                     "launch, kernel %s)" % (tag, d.get("kernel", "?")))
     except (OSError, KeyError, ValueError):
-        return None
+        return None, "no capture committed"
 
 
 class ClockSampler:
@@ -132,23 +180,41 @@ class ClockSampler:
         return out
 
 
-def make_host_batches(rank):
-    """N_INPUT_SETS pinned (8, 40000, 3+C) float32 batches; seeds differ per rank and per set."""
+def make_host_batches(rank, world):
+    """n_input_sets pinned (scenes, 40000, 3+C) float32 batches; seeds differ per rank and per set."""
     from spacap3d_b200.scenes import make_scene
     sets = []
-    for s in range(N_INPUT_SETS):
-        scenes = [make_scene(1000 * CONFIG_ID + 100 * rank + 10 * s + i, N_POINTS, use_height=True)
-                  for i in range(SCENES_PER_GPU)]
+    for s in range(n_input_sets(world)):
+        scenes = [make_scene(1000 * CFG["id"] + 100 * rank + 10 * s + i, N_POINTS, **CFG["scene_kw"])
+                  for i in range(scenes_per_gpu(world))]
         t = torch.from_numpy(np.stack(scenes, 0))
         sets.append(t.pin_memory() if torch.cuda.is_available() else t)
     return sets
 
 
+def checkpoint_file():
+    """The reference's pretrained VoteNet weights for this config's channel count, when staged (a data file)."""
+    names = {1: "PRETRAIN_VOTENET_XYZ", 7: "PRETRAIN_VOTENET_XYZ_COLOR_NORMAL",
+             132: "PRETRAIN_VOTENET_XYZ_MULTIVIEW_NORMAL"}
+    p = os.path.join(ROOT, "baseline", "_ref", "pretrained", names.get(CFG["feature_dim"], "-"), "model.pth")
+    return p if os.path.exists(p) else None
+
+
+def weights_note():
+    p = checkpoint_file()
+    return ("reference checkpoint pretrained/%s/model.pth" % os.path.basename(os.path.dirname(p))) if p else \
+        "random init (seed 0)"
+
+
 def make_detector(device):
     from spacap3d_b200.detector import VoteNetDetector
     torch.manual_seed(0)
-    model = VoteNetDetector(input_feature_dim=FEATURE_DIM).to(device).eval()
-    return model
+    model = VoteNetDetector(input_feature_dim=CFG["feature_dim"])
+    p = checkpoint_file()
+    if p:
+        missing, unexpected = model.load_state_dict(torch.load(p, map_location="cpu"), strict=False)
+        assert not missing and not unexpected, (missing, unexpected)
+    return model.to(device).eval()
 
 
 RESULT_KEYS = ("objectness_scores", "center", "size_scores", "size_residuals", "sem_cls_scores",
@@ -316,119 +382,147 @@ def hbm_bound_ops(pc, flush, hbm_peak):
     return out
 
 
+def bind_rank_cpus(local, world):
+    """One disjoint core set per local rank (the ranks of one box otherwise share every core and the
+    submit / copy threads of 8 ranks migrate over each other: e2e scaled 0.886 at 8 GPUs in round 1)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // world
+        if world > 1 and per >= 2:
+            mine = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            torch.set_num_threads(max(1, min(per, 4)))
+            return mine
+    except (AttributeError, OSError):
+        pass
+    return None
+
+
+def init_dist(local, device, world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+        return dist, (lambda: dist.barrier(device_ids=[local]))
+    return None, (lambda: None)
+
+
+def region_stats(regions_ms):
+    return {"repeats": len(regions_ms), "median_ms": round(statistics.median(regions_ms), 4),
+            "min_ms": round(min(regions_ms), 4), "max_ms": round(max(regions_ms), 4)}
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
-        barrier = lambda: dist.barrier(device_ids=[local])
-    else:
-        dist = None
-        barrier = lambda: None
+    cpus = bind_rank_cpus(local, world)
+    dist, barrier = init_dist(local, device, world)
     from spacap3d_b200 import _lib
     _lib.load()
+    if CFG["id"] == 5:
+        return run_train(args, rank, world, local, device, dist, barrier)
     meter = KernelMeter()
     meter.install()
     model = make_detector(device)
-    host = make_host_batches(rank)
+    host = make_host_batches(rank, world)
+    n_sets = len(host)
+    spg = scenes_per_gpu(world)
     resident = [h.to(device) for h in host]
     flush = L2Flusher(device)
+    batch_mb = host[0].numel() * host[0].element_size() / 1e6
 
-    # ---- (1) value: inputs resident in HBM ------------------------------------------------------
+    # ---- (1) eager single-stream pass: inputs resident in HBM, L2 flushed between steps -------------
     out_holder = {}
 
     def step_resident(i):
-        out_holder["o"] = forward_resident(model, resident[i % N_INPUT_SETS])
+        out_holder["o"] = forward_resident(model, resident[i % n_sets])
 
     meter.launches = 0
     eager_steps = args.steps if args.mode == "eager" else min(args.steps, 60)
     eager_warm = args.warmup if args.mode == "eager" else min(args.warmup, 12)
     per_step, wall, clocks = timed_loop(step_resident, eager_steps, eager_warm, flush, barrier,
-                                        ClockSampler(local))
+                                        ClockSampler(local) if args.mode == "eager" else None)
     launches_per_step = meter.launches // (eager_steps + eager_warm)
     dev_s = sum(per_step) / 1e3
+    regions = None
 
     eager = {"ms_per_step": round(dev_s / eager_steps * 1e3, 4),
-             "scenes_per_s_per_gpu": round(SCENES_PER_GPU * eager_steps / dev_s, 2),
+             "scenes_per_s_per_gpu": round(spg * eager_steps / dev_s, 2),
              "note": "no CUDA graph, single stream, 256 MiB L2 flush between steps (excluded from the timing)"}
     graph_info = None
     if args.mode == "graph":
         # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
         from spacap3d_b200.pipeline import GraphedDetector
-        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS,
-                                 fps_cull=int(os.environ.get("SPC_BENCH_FPS_CULL", "2")),
-                                 sa_min_tiles=int(os.environ.get("SPC_BENCH_SA_MIN_TILES", "16")))
-        # the knobs are baked into the captured graphs; eager passes stay on the single-call defaults
-        _lib.call("spc_set_fps_cluster", 0)
-        _lib.call("spc_set_fps_cull", 0)
-        _lib.call("spc_set_sa_min_tiles", 0)
+        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS)
 
-        def timed_graph(submit, steps, warmup, sampler=None):
-            # nvidia-smi needs ~0.2 s to deliver its first sample and the timed region of the default run lasts
-            # ~0.2 s: the sampler runs from the first warm-up step on, and if it still has fewer than 4 samples when
-            # the timed region ends, the SAME workload keeps running untimed until it has (reported as
-            # extra_untimed_steps), so the clocks are always taken under this load
+        def timed_graph(submit, steps, warmup, repeats, sampler=None):
+            """`repeats` timed regions of exactly `steps` submits each, every region bracketed by a barrier +
+            synchronize on both sides and timed with CUDA events (start event forked into every stream, end
+            event after joining them).  nvidia-smi needs ~0.2 s for its first sample, so the sampler runs from
+            the first warm-up step on and, if it still has fewer than 4 samples when the regions are done, the
+            SAME workload keeps running untimed until it has (reported as extra untimed steps)."""
             if sampler:
                 sampler.start()
             for i in range(warmup):
                 submit(i)
             runner.wait_all()
-            torch.cuda.synchronize()
-            barrier()
             cur = torch.cuda.current_stream()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            out, n = [], warmup
             t0 = time.perf_counter()
-            e0.record(cur)
-            runner.fork_from(e0)
-            for k in range(steps):
-                submit(warmup + k)
-            runner.join_into(cur)
-            e1.record(cur)
-            torch.cuda.synchronize()
+            for _ in range(repeats):
+                torch.cuda.synchronize()
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+                runner.fork_from(e0)
+                for k in range(steps):
+                    submit(n + k)
+                n += steps
+                runner.join_into(cur)
+                e1.record(cur)
+                torch.cuda.synchronize()
+                barrier()
+                out.append(e0.elapsed_time(e1))
             wall_ = time.perf_counter() - t0
-            barrier()
             clk = None
             if sampler:
                 extra, t_end = 0, time.perf_counter() + 3.0
                 while sampler.count() < 4 and time.perf_counter() < t_end:
                     for q in range(50):
-                        submit(warmup + steps + extra + q)
+                        submit(n + extra + q)
                     extra += 50
                     runner.wait_all()
                 clk = sampler.stop()
-                clk["window"] = "warm-up + timed region + %d extra untimed steps of the same workload" % extra
-            return e0.elapsed_time(e1) / 1e3, wall_, clk
+                clk["window"] = ("warm-up + %d timed regions + %d extra untimed steps of the same workload"
+                                 % (repeats, extra))
+            return out, wall_, clk
 
-        dev_s, wall, clocks = timed_graph(lambda i: runner.submit(resident[i % N_INPUT_SETS]),
-                                          args.steps, args.warmup, ClockSampler(local))
+        regions, wall, clocks = timed_graph(lambda i: runner.submit(resident[i % n_sets]),
+                                            args.steps, args.warmup, REPEATS, ClockSampler(local))
 
         def submit_e2e(i):
             slot = runner._next
-            if i >= N_STREAMS:
+            if runner.busy(slot):
                 runner.wait(slot)                     # results of the previous use of this slot are on the host
-            runner.submit(host[i % N_INPUT_SETS], to_host=True)
+            runner.submit(host[i % n_sets], to_host=True)
 
-        e2e_graph_s, _, _ = timed_graph(submit_e2e, args.steps, args.warmup)
-        graph_info = {"streams": N_STREAMS, "e2e_s": e2e_graph_s}
+        e2e_regions, _, _ = timed_graph(submit_e2e, args.steps, args.warmup, REPEATS)
+        graph_info = {"streams": N_STREAMS, "e2e_regions": e2e_regions}
+        runner.close()
 
-    # ---- (2) e2e: pinned host -> device -> forward -> device -> host ---------------------------
+    # ---- (2) eager e2e: pinned host -> device -> forward -> device -> host ----------------------
     d2h_bytes = [0]
 
     def step_e2e(i):
-        pc = host[i % N_INPUT_SETS].to(device, non_blocking=True)
+        pc = host[i % n_sets].to(device, non_blocking=True)
         o = forward_resident(model, pc)
         res = [o[k].to("cpu", non_blocking=False) for k in RESULT_KEYS]
         d2h_bytes[0] = sum(r.numel() * r.element_size() for r in res)
 
     e2e_steps, e2e_wall, _ = timed_loop(step_e2e, args.steps if graph_info is None else min(args.steps, 5),
-                                        args.warmup, flush, barrier)
-    e2e_s = sum(e2e_steps) / 1e3
-    eager["e2e_ms_per_step"] = round(e2e_s / len(e2e_steps) * 1e3, 4)
-    if graph_info is not None:
-        e2e_s = graph_info["e2e_s"]
+                                        args.warmup if graph_info is None else 3, flush, barrier)
+    eager["e2e_ms_per_step"] = round(sum(e2e_steps) / len(e2e_steps), 4)
     h2d_bytes = host[0].numel() * host[0].element_size()
 
     # ---- (3) per-kernel event timing (separate pass so the events do not perturb (1)) ----------
@@ -442,12 +536,19 @@ def run_ours(args):
     agg = meter.summary(prof_steps)
     meter.uninstall()
 
-    # max over ranks
+    # ---- reduce over ranks: every region's time is the max over ranks, then the median region -------
+    if graph_info is not None:
+        t = torch.tensor([regions, graph_info["e2e_regions"]], device=device, dtype=torch.float64)
+    else:
+        t = torch.tensor([[dev_s * 1e3], [sum(e2e_steps)]], device=device, dtype=torch.float64)
     if dist is not None:
-        t = torch.tensor([dev_s, e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, e2e_s = float(t[0]), float(t[1])
-    total_scenes = SCENES_PER_GPU * world * args.steps
+    dev_regions, e2e_regions = t[0].tolist(), t[1].tolist()
+    steps_in_region = args.steps if graph_info is not None else eager_steps
+    dev_s = statistics.median(dev_regions) / 1e3
+    e2e_s = statistics.median(e2e_regions) / 1e3
+    e2e_steps_in_region = args.steps if graph_info is not None else len(e2e_steps)
+    total_scenes = spg * world * steps_in_region
     hbm_peak, tf_peak, peak_src = peaks()
 
     ops = {}
@@ -473,34 +574,43 @@ def run_ours(args):
         tensor_bound = avg_flops / (tf_peak * 1e12) > avg_bytes / (hbm_peak * 1e9)
         if tensor_bound:
             achieved = avg_flops / (avg_ms * 1e-3) / 1e12
+        traffic, traffic_src = ncu_traffic("sa_fused", "sa_fused.cu")
         roofline = {"kernel": name.replace("spc_", "").replace("_ex", ""), "bound": "tensor" if tensor_bound else "hbm",
                     "achieved": round(achieved, 2),
                     "peak": tf_peak if tensor_bound else hbm_peak,
                     "unit": "TFLOP/s" if tensor_bound else "GB/s",
                     "frac": round(achieved / (tf_peak if tensor_bound else hbm_peak), 4),
                     "algo_flops_per_launch": int(avg_flops),
-                    "traffic": ncu_traffic("sa_fused"), "traffic_source": "profiles/r1_sa_fused_traffic.json (ncu --set full, "
-                    "dram read+write per launch, mean of the step's %d launches)" % (d["launches"] // prof_steps),
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src,
                     "launches_per_step": d["launches"] // prof_steps,
                     "avg_launch_us": round(avg_ms * 1e3, 2), "algo_bytes_per_launch": int(avg_bytes),
                     "share_of_step": round(d["ms"] / prof_steps / eager["ms_per_step"], 4),
                     "share_of": "eager single-stream step (kernels of different batches overlap in graph mode)"}
-    # the sequential sampler of the raw cloud (SA1): args = (xyz, B, N, npoint, ...); the later FPS calls
-    # run on FPS-ordered inputs and mostly take the verified shortcut, so they are not "rounds"
-    fps_recs = [r for r in meter.records if r[0] in ("spc_furthest_point_sampling", "spc_furthest_point_sampling_ex")]
-    latency_bound = None
-    if fps_recs:
-        n_max = max(r[4][2] for r in fps_recs)
-        big = [r for r in fps_recs if r[4][2] == n_max]
-        ms = sum(r[2].elapsed_time(r[3]) for r in big)
-        rounds = sum(max(r[4][3] - 1, 0) for r in big)
-        latency_bound = {"kernel": "furthest_point_sampling (N=%d -> %d)" % (n_max, big[0][4][3]),
-                         "ms_per_step": round(ms / prof_steps, 4),
-                         "us_per_round": round(ms * 1e3 / max(rounds, 1), 4),
-                         "sequential_rounds_per_step": rounds // prof_steps,
-                         "note": "latency-bound by construction (each round depends on the previous pick); "
-                                 "timed with the single-call kernel (culling off)"}
+    # the kernel with the largest time share, whatever bounds it.  For the sequential sampler of the raw cloud (SA1;
+    # args = (xyz, B, N, npoint, ...)) the meaningful figures are us per round and the SM-time a scene occupies; the
+    # later FPS calls run on FPS-ordered inputs and mostly take the verified shortcut, so they are not "rounds"
+    dominant = None
+    if agg:
+        name, d = max(agg.items(), key=lambda kv: kv[1]["ms"])
+        dominant = {"kernel": name.replace("spc_", ""), "ms_per_step": round(d["ms"] / prof_steps, 4),
+                    "launches_per_step": d["launches"] // prof_steps,
+                    "share_of_step": round(d["ms"] / prof_steps / eager["ms_per_step"], 4),
+                    "share_of": "eager single-stream step"}
+        fps_recs = [r for r in meter.records if r[0].startswith("spc_furthest_point_sampling")]
+        if name.startswith("spc_furthest_point_sampling") and fps_recs:
+            n_max = max(r[4][2] for r in fps_recs)
+            big = [r for r in fps_recs if r[4][2] == n_max]
+            ms = sum(r[2].elapsed_time(r[3]) for r in big)
+            rounds = sum(max(r[4][3] - 1, 0) for r in big)
+            dominant.update({
+                "bound": "latency (each round depends on the previous pick; no HBM traffic inside the rounds)",
+                "what": "furthest_point_sampling N=%d -> %d" % (n_max, big[0][4][3]),
+                "us_per_round": round(ms * 1e3 / max(rounds, 1), 4),
+                "sequential_rounds_per_step": rounds // prof_steps,
+                "single_call_ms": round(ms / len(big), 4),
+                "note": "timed with the single-call kernel configuration; the graph pipeline uses the throughput "
+                        "configuration (see config.fps)"})
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -508,30 +618,118 @@ def run_ours(args):
     hbm_ops = hbm_bound_ops(resident[0], flush, hbm_peak) if rank == 0 and world == 1 else None
 
     if rank == 0:
+        cfg = workload_config(world)
+        cfg.update({
+            "precision": "shared-MLP 1x1 convs in fp16 on tcgen05 with fp32 accumulation; point ops fp32/int32",
+            "l2": ("inputs larger than L2: %d distinct batches (%.0f MB) rotated; " % (n_sets, n_sets * batch_mb)) +
+                  ("CUDA-graph replay on %d streams (batches overlap, no flush possible between them)" % N_STREAMS
+                   if graph_info is not None else "256 MiB L2 flush between timed steps"),
+            "execution": ("cuda-graph x %d streams" % N_STREAMS) if graph_info is not None else "eager, 1 stream",
+            "parallelism": "scenes sharded by batch, %d rank(s), no collective" % world,
+            "cpu_affinity": ("%d cores per rank" % len(cpus)) if cpus else "inherited"})
         line = {
             "metric": "detector scenes/s @40k pts", "value": round(total_scenes / dev_s, 3),
             "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(dev_s / args.steps * 1e3, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
-                       "input_feature_dim": FEATURE_DIM, "weights": "random init (seed 0), eval mode",
-                       "precision": "shared-MLP 1x1 convs in bf16 on tcgen05 with fp32 accumulation; point ops fp32/int32",
-                       "l2": ("inputs larger than L2: %d distinct batches (%.0f MB) rotated; " % (N_INPUT_SETS, N_INPUT_SETS * 5.12)) +
-                             ("CUDA-graph replay on %d streams (batches overlap, no flush possible between them)" % N_STREAMS
-                              if graph_info is not None else "256 MiB L2 flush between timed steps"),
-                       "execution": ("cuda-graph x %d streams" % N_STREAMS) if graph_info is not None else "eager, 1 stream",
-                       "parallelism": "scenes sharded by batch, %d rank(s), no collective" % world},
-            "e2e": {"value": round(total_scenes / e2e_s, 3), "unit": "scenes/s",
+            "ms_per_step": round(dev_s / steps_in_region * 1e3, 4), "higher_is_better": True,
+            "scaling": CFG["scaling"], "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": cfg,
+            "timed_regions": {"what": "%d regions of exactly %d steps, each bracketed by barrier + synchronize; "
+                                      "value = median region" % (len(dev_regions), steps_in_region),
+                              "device": region_stats(dev_regions), "e2e": region_stats(e2e_regions)},
+            "e2e": {"value": round(spg * world * e2e_steps_in_region / e2e_s, 3), "unit": "scenes/s",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes[0]),
-                    "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+                    "ms_per_step": round(e2e_s / e2e_steps_in_region * 1e3, 4)},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
-            "roofline": roofline, "hbm_ops": hbm_ops, "latency_bound": latency_bound, "ops": ops,
+            "roofline": roofline, "dominant": dominant, "hbm_ops": hbm_ops, "ops": ops,
             "kernel_ms_per_step": round(step_ms_kernels, 4),
             "eager": eager,
             "cpu_baseline": cpu_base, "clocks": clocks,
             "wall_s_timed_region": round(wall, 4),
         }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_train(args, rank, world, local, device, dist, barrier):
+    """BASELINE config 5: forward + backward of the detector in training mode (autograd through the unfused
+    sm_100a kernels and their backward passes + cuDNN convolutions + the fused BN/ReLU/max-pool training kernels)
+    and ONE flat NCCL all-reduce of the gradients per step (the reference: nn.DataParallel, scripts/train.py:198-200).
+    The loss is a surrogate (mean square of the head outputs): lib/loss_helper.py is outside the path."""
+    from tools import bench_train
+    from spacap3d_b200.scenes import make_scene
+    n, spg = args.points, scenes_per_gpu(world)
+    scale = max(1, round(n / 40000))
+    model = bench_train.build_model(scale, device)
+    n_sets = 3
+    host = [torch.from_numpy(np.stack([make_scene(5000 + 100 * rank + 10 * s + i, n, **CFG["scene_kw"])
+                                       for i in range(spg)], 0)).pin_memory() for s in range(n_sets)]
+    resident = [h.to(device) for h in host]
+    flush = L2Flusher(device)
+    ar_events = []
+
+    def step(pc, timed_ar=False):
+        model.zero_grad(set_to_none=True)
+        out = model({"point_clouds": pc})
+        loss = bench_train.surrogate_loss(out)
+        loss.backward()
+        if world > 1:
+            from spacap3d_b200.dist import allreduce_gradients
+            if timed_ar:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                allreduce_gradients(model)
+                e1.record()
+                ar_events.append((e0, e1))
+            else:
+                allreduce_gradients(model)
+        return loss
+
+    from spacap3d_b200 import _lib
+    launches = [0]
+    orig = _lib.call
+
+    def counting(name, *a):
+        launches[0] += 1
+        return orig(name, *a)
+    _lib.call = counting
+    per_step, wall, clocks = timed_loop(lambda i: step(resident[i % n_sets], True), args.steps, args.warmup, flush,
+                                        barrier, ClockSampler(local))
+    launches_per_step = launches[0] // (args.steps + args.warmup)
+    _lib.call = orig
+    loss_holder = {}
+
+    def step_e2e(i):
+        pc = host[i % n_sets].to(device, non_blocking=True)
+        loss_holder["l"] = float(step(pc))              # device -> host read of the loss
+
+    e2e_steps, _, _ = timed_loop(step_e2e, args.steps, args.warmup, flush, barrier)
+    t = torch.tensor([sum(per_step), sum(e2e_steps)], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, e2e_s = float(t[0]) / 1e3, float(t[1]) / 1e3
+    ar_us = [a.elapsed_time(b) * 1e3 for a, b in ar_events[-args.steps:]] if ar_events else []
+    n_params = sum(p.numel() for p in model.parameters())
+    if rank == 0:
+        cfg = workload_config(world)
+        cfg.update({"points": n, "sa_npoint_scale": scale, "mode": "training: forward + backward + gradient all-reduce",
+                    "weights": "random init (seed 0), train mode",
+                    "l2": "256 MiB L2 flush between timed steps", "execution": "eager, 1 stream",
+                    "parallelism": "scenes sharded by batch, %d rank(s), one flat NCCL all-reduce of %d gradients "
+                                   "(%.1f MB) per step" % (world, n_params, n_params * 4 / 1e6)})
+        line = {"metric": "detector training scenes/s (fwd+bwd+allreduce)", "value": round(spg * world * args.steps / dev_s, 3),
+                "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(dev_s / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "e2e": {"value": round(spg * world * args.steps / e2e_s, 3), "unit": "scenes/s",
+                        "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 4,
+                        "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
+                "allreduce": {"median_us": round(statistics.median(ar_us), 1) if ar_us else None,
+                              "bytes": n_params * 4, "note": "CUDA events around dist.allreduce_gradients on rank 0 "
+                              "(includes waiting for the slowest rank's backward)"},
+                "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
+                "roofline": None, "cpu_baseline": None, "clocks": clocks, "wall_s_timed_region": round(wall, 4)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -634,7 +832,7 @@ def cpu_baseline(model_gpu, budget_s=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     model = copy.deepcopy(model_gpu).to("cpu").eval()
-    scenes = [torch.from_numpy(make_scene(1000 + i, N_POINTS, use_height=True)[None]) for i in range(2)]
+    scenes = [torch.from_numpy(make_scene(1000 + i, N_POINTS, **CFG["scene_kw"])[None]) for i in range(2)]
     n, t0 = 0, time.perf_counter()
     with swapped_ops(OracleOps(), host_decode=False), torch.no_grad():
         model({"point_clouds": scenes[0]})          # warm-up (page-in, thread pools)
@@ -651,58 +849,77 @@ def cpu_baseline(model_gpu, budget_s=12.0):
 
 
 def run_reference(args):
+    """Reference arm: the reference's UNMODIFIED Python stack (SpaCapNet detection branch, models/*.py,
+    lib/pointnet2/*.py staged under baseline/_ref) on its own CUDA extension (oracle/_ref), one replica per rank,
+    same workload config, same weights; timed like the eager pass of our arm (CUDA events per step, L2 flush between
+    steps).  Falls back to the CPU oracle port when the stack or the extension is not loadable."""
     rank, world, local = dist_env()
-    if rank != 0:
+    stack, why = None, ""
+    if CFG["id"] == 5:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "config 5 (training sweep) has no reference arm in "
+                              "bench.py; tools/bench_train.py --ref times the reference extension on the same step"}))
         return
-    ref = None
-    why = ""
     if torch.cuda.is_available():
         try:
-            from oracle.build_ref import load_ref
-            ref = load_ref()
+            from oracle import refstack
+            stack = refstack.load_stack("reference")
         except Exception as e:  # noqa: BLE001
-            why = "oracle/_ref not loadable (%s); CPU port used" % type(e).__name__
+            why = "reference stack not loadable (%s: %s); CPU port used" % (type(e).__name__, str(e)[:80])
     else:
         why = "no GPU; CPU port used"
-    config = {"workload": WORKLOAD, "scenes_per_gpu": SCENES_PER_GPU, "points": N_POINTS,
-              "input_feature_dim": FEATURE_DIM, "weights": "random init (seed 0), eval mode"}
-    if ref is not None:
+    config = workload_config(world)
+    spg = scenes_per_gpu(world)
+    if stack is not None:
+        from oracle import refstack
         torch.cuda.set_device(local)
         device = torch.device("cuda", local)
-        model = make_detector(device)
-        host = make_host_batches(rank)
+        dist, barrier = init_dist(local, device, world)
+        model = refstack.build_detector(stack, CFG["feature_dim"], device, pretrained=checkpoint_file() is not None)
+        if checkpoint_file() is None:
+            ours = make_detector("cpu")                   # same random weights as our arm
+            model.load_state_dict(ours.state_dict(), strict=True)
+        host = make_host_batches(rank, world)
+        n_sets = len(host)
         resident = [h.to(device) for h in host]
         flush = L2Flusher(device)
-        with swapped_ops(ref, host_decode=True):
-            def step(i):
-                forward_resident(model, resident[i % N_INPUT_SETS])
-            per_step, wall, clocks = timed_loop(step, args.steps, args.warmup, flush, lambda: None,
-                                                ClockSampler(local))
-        s = sum(per_step) / 1e3
-        val = SCENES_PER_GPU * args.steps / s
-        config["l2"] = "256 MiB L2 flush between timed steps"
-        config["arm"] = ("reference CUDA ops (lib/pointnet2/_ext_src rebuilt unmodified for sm_100a) in the "
-                         "reference op sequence + cuDNN MLP (torch defaults, TF32 conv) + host box decode; "
-                         "runs on rank 0 / one GPU only (the other ranks exit)")
-        line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 3),
-                "unit": "scenes/s", "n_gpus": world, "ranks_used": 1, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(s / args.steps * 1e3, 4), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config, "device": "cuda",
-                "cpu_baseline": {"value": round(val, 3), "unit": "scenes/s", "cores": 0, "kind": "reference",
-                                 "sample": "%d steps x 8 scenes on the GPU (the reference has no CPU path: "
-                                           "'CPU not supported', sampling.cpp:33-35)" % args.steps},
-                "e2e": {"value": round(val, 3), "unit": "scenes/s", "h2d_bytes_per_step": 0,
-                        "d2h_bytes_per_step": 0},
-                "clocks": clocks}
-        print(json.dumps(line))
+
+        def step(i):
+            forward_resident(model, resident[i % n_sets])
+        per_step, wall, clocks = timed_loop(step, args.steps, args.warmup, flush, barrier, ClockSampler(local))
+        t = torch.tensor([sum(per_step)], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = float(t[0]) / 1e3
+        val = spg * world * args.steps / s
+        if rank == 0:
+            line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 3),
+                    "unit": "scenes/s", "n_gpus": world, "ranks_used": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": round(s / args.steps * 1e3, 4), "higher_is_better": True,
+                    "scaling": CFG["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": config, "device": "cuda",
+                    "arm": "UNMODIFIED reference stack (baseline/_ref: models/SpaCapNet.py detection branch, "
+                           "backbone/voting/proposal modules, lib/pointnet2/*.py, host-side box decode) on the "
+                           "reference's CUDA ops rebuilt for sm_100a (oracle/_ref); torch defaults (TF32 convs); "
+                           "eager, one replica per rank, 256 MiB L2 flush between timed steps",
+                    "cpu_baseline": {"value": round(val, 3), "unit": "scenes/s", "cores": 0, "kind": "reference",
+                                     "sample": "%d steps x %d scenes per GPU on the GPU (the reference has no CPU "
+                                               "path: 'CPU not supported', sampling.cpp:33-35)" % (args.steps, spg)},
+                    "e2e": {"value": round(val, 3), "unit": "scenes/s", "h2d_bytes_per_step": 0,
+                            "d2h_bytes_per_step": 0},
+                    "clocks": clocks}
+            print(json.dumps(line))
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    if rank != 0:
         return
     # CPU port: bounded sample = `steps` single-scene forwards
     model = make_detector("cpu")
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     from spacap3d_b200.scenes import make_scene
-    scene = torch.from_numpy(make_scene(1000, N_POINTS, use_height=True)[None])
+    scene = torch.from_numpy(make_scene(1000, N_POINTS, **CFG["scene_kw"])[None])
     steps = max(1, min(args.steps, 5))
     with swapped_ops(OracleOps(), host_decode=True), torch.no_grad():
         for _ in range(min(args.warmup, 1)):
@@ -712,12 +929,11 @@ def run_reference(args):
             model({"point_clouds": scene})
         el = time.perf_counter() - t0
     val = steps / el
-    config["arm"] = "CPU oracle port, batch 1 per step; " + why
     line = {"impl": "reference", "metric": "detector scenes/s @40k pts", "value": round(val, 4),
             "unit": "scenes/s", "n_gpus": world, "ranks_used": 1, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": round(el / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(el / steps * 1e3, 3), "higher_is_better": True, "scaling": CFG["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "device": "cpu",
+            "device": "cpu", "arm": "CPU oracle port, batch 1 per step; " + why,
             "cpu_baseline": {"value": round(val, 4), "unit": "scenes/s", "cores": cores, "kind": "port",
                              "sample": "%d single-scene forwards" % steps},
             "e2e": {"value": round(val, 4), "unit": "scenes/s", "h2d_bytes_per_step": 0,
@@ -726,12 +942,14 @@ def run_reference(args):
 
 
 def main():
-    global N_STREAMS
+    global N_STREAMS, CFG, N_POINTS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json workload")
+    ap.add_argument("--points", type=int, default=N_POINTS, help="points per scene (config 5: 40000..200000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=N_STREAMS, help="graph replay streams (batches in flight)")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
@@ -739,6 +957,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     N_STREAMS = max(1, args.streams)
+    CFG = dict(CONFIGS[args.config], id=args.config)
+    if args.config != 5:
+        N_POINTS = args.points
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -54,27 +54,26 @@ int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint, int3
  * rounds, all others run the normal kernel.  Results are identical to spc_furthest_point_sampling
  * in every case; the hint only affects speed. */
 size_t spc_fps_workspace_bytes(int B, int N, int npoint);
-/* Tuning knob, process-wide: CTAs per scene cluster for large clouds (0 = automatic = 8).  Does not
- * change results.  4 halves the SM-time per call (throughput with several batches in flight), 8
- * minimises the latency of a single call. */
-int spc_set_fps_cluster(int cluster_ctas);
-/* Tuning knob, process-wide: 1 = clouds of 8192..40960 points that come with a workspace
- * (spc_furthest_point_sampling_ex) are first sorted along a Morton curve and every warp then skips
- * the rounds whose new centre provably cannot lower any of its points' min-distances (bounding-box
- * test, conservative in fp32).  Results are identical; a single call is ~15 % slower, several calls
- * in flight on different streams finish sooner (fewer instructions issued).  Default 0. */
-/* Modes: 1 = coordinates and min-distances in registers (two 256-thread CTAs per SM); 2 = coordinates in shared
- * memory (three CTAs per SM; what the graph pipeline uses); 3 = "full-SM" CTAs of 768 threads in clusters of
- * ceil(N/15360) (a 40 k-point scene holds exactly 3 SMs; measured 7 % slower than mode 2 in the 16-stream pipeline:
- * 24 warps per reduction level make a round slower than three independent 8-warp CTAs). */
-int spc_set_fps_cull(int on);
+/* Sampler selection, PER CALL (spc_furthest_point_sampling_ex2; the library keeps no mutable state).  Results are
+ * identical for every choice.
+ *   SPC_FPS_AUTO     the library decides: the bucketed sampler for 4096 <= N <= 40960 when a workspace is given,
+ *                    otherwise the cluster sampler (small clouds: a single CTA).
+ *   SPC_FPS_CLUSTER  one thread-block cluster per scene; coordinates and running min-distances of every point in
+ *                    registers / distributed shared memory, per-round arg-max over warp shuffles + DSMEM
+ *                    (needs no workspace; holds 4 SMs per 40 k-point scene while it runs).
+ *   SPC_FPS_BUCKET   one 256-thread CTA per scene; Morton-sorted points parked in L2 (workspace), per-bucket
+ *                    bounding boxes and candidates in shared memory, only the buckets a new centre can change are
+ *                    updated (four scenes share an SM).  SPC_ERR_UNSUPPORTED outside its size range. */
+#define SPC_FPS_AUTO 0
+#define SPC_FPS_CLUSTER 1
+#define SPC_FPS_BUCKET 2
 int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                    float *new_xyz, int hint_ordered, void *workspace,
                                    size_t workspace_bytes, void *stream);
 /* Same, with the "strict sequence" side channel that lets a chain of samplers (SA1 -> SA2 -> SA3 -> SA4 each
  * sample from the previous output, models/backbone_module.py:107-127) skip even the proof kernels:
  *   strict_out    (B) int32 device, nullable: 1 = every pick of THIS call was the strict unique maximum of the
- *                 min-distances (tracked exactly by the culled kernels, implied by a successful proof), so FPS over
+ *                 min-distances (implied by a successful proof; the samplers themselves report 0 = unknown), so FPS over
  *                 any prefix of the output is provably the identity; 0 = a tie occurred or it was not tracked.
  *   known_ordered (B) int32 device, nullable: strict_out of the call that produced `xyz` (npoint <= N);
  *                 scenes flagged 1 skip the proof and the sequential rounds, the others behave as with
@@ -82,7 +81,7 @@ int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint, i
 int spc_furthest_point_sampling_ex2(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                     float *new_xyz, int hint_ordered, const int32_t *known_ordered,
                                     int32_t *strict_out, void *workspace, size_t workspace_bytes,
-                                    void *stream);
+                                    int algo, void *stream);
 
 /* gather_points(points, idx)                             sampling.cpp:15-38, sampling_gpu.cu:8-30
  * points (B,C,N), idx (B,M) -> out (B,C,M) */
@@ -146,46 +145,43 @@ int spc_three_interpolate(const float *points, const int32_t *idx, const float *
 int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const float *weight,
                                int B, int C, int n, int m, float *grad_points, void *stream);
 
-/* Tuning knob, process-wide (0 = one CTA per SM, the latency optimum): give every CTA of the fused
- * set-abstraction kernel at least this many 128-row tiles, i.e. launch fewer CTAs for the small layers.
- * Results do not change.  With several batches in flight the freed SMs run other streams' kernels:
- * +4.5 % scenes/s at 16 on B200 (12 streams), -6 % for a single stream. */
-int spc_set_sa_min_tiles(int tiles_per_cta);
-
 /* Fused set-abstraction forward, eval mode (no reference C++ counterpart: it replaces the whole
  * Python/ATen/cuDNN sequence of PointnetSAModuleVotes.forward after the ball query --
  * pointnet2_utils.py:351-362 (2x group_points, sub, div, cat), pytorch_utils.py:11-36 (SharedMLP =
  * 3 x [1x1 conv, BN, ReLU]) and pointnet2_modules.py:256-271 (max-pool over nsample)).
  *   xyz (B,n,3), new_xyz (B,npoint,3), idx (B,npoint,nsample) from spc_ball_query.
  *   Layer 0, one of two forms (BatchNorm folded into weights/bias by the caller):
- *     in-line  : G_bf16 == NULL; feat (B,Cf,n) raw features (Cf <= 16, NULL when Cf == 0),
+ *     in-line  : G_f16 == NULL; feat (B,Cf,n) raw features (Cf <= 16, NULL when Cf == 0),
  *                W0 (C1,3+Cf), b0 (C1);  h1 = relu(W0 . [(p-c)/radius, f] + b0)
- *     projected: G_bf16 (B,n,C1) BF16 = W0[:,3:] . f per POINT (one plain GEMM by the caller, conv0 is
+ *     projected: G_f16 (B,n,C1) FP16 = W0[:,3:] . f per POINT (one plain GEMM by the caller, conv0 is
  *                linear), Cf == 0, W0 (C1,3) = the xyz columns, b0 (C1);
  *                h1 = relu(G[idx] + W0 . (p-c)/radius + b0), the xyz term evaluated in fp32 here
- *   Layers 1,2: W1 (C2,C1), W2 (C3,C2) row-major BF16 (device pointers to 16-bit data), b1, b2 f32;
+ *   Layers 1,2: W1 (C2,C1), W2 (C3,C2) row-major FP16 (device pointers to 16-bit data), b1, b2 f32;
  *   run on tcgen05 tensor cores, fp32 accumulation in TMEM.
- *   out (B,C3,npoint) f32 = max over nsample of relu(layer2); out_pm_bf16 (optional, may be NULL):
- *   the same values as (B,npoint,C3) BF16, point-major (input of the next layer's projection GEMM).
+ *   out (B,C3,npoint) f32 = max over nsample of relu(layer2); out_pm_f16 (optional, may be NULL):
+ *   the same values as (B,npoint,C3) FP16, point-major (input of the next layer's projection GEMM).
  * Returns SPC_ERR_UNSUPPORTED (nothing launched) for shapes without a kernel: supported are
  * (C1,C2,C3) in {(64,64,128),(128,128,128),(128,128,256)}, nsample in {16,32,64},
  * npoint*nsample % 128 == 0. */
 int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *idx,
-                         const void *G_bf16, const float *feat, const float *W0, const float *b0,
-                         int Cf, float radius, const void *W1_bf16, const float *b1,
-                         const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample,
-                         int C1, int C2, int C3, float *out, void *out_pm_bf16, void *stream);
+                         const void *G_f16, const float *feat, const float *W0, const float *b0,
+                         int Cf, float radius, const void *W1_f16, const float *b1,
+                         const void *W2_f16, const float *b2, int B, int n, int npoint, int nsample,
+                         int C1, int C2, int C3, float *out, void *out_pm_f16, void *stream);
 /* Same, plus optional HOST copies of the folded layer-0 weights (W0_host (C1,3+Cf), b0_host (C1); host memory, read
  * during the call; NULL = not available).  In the in-line form with C1*(4+Cf) <= 768 the kernel then takes them by
  * value through its parameters (constant bank) instead of staging W0 in shared memory.  Results are the same up to
- * fp32 summation order (the bias is the first addend instead of the last). */
-int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_t *idx, const void *G_bf16,
+ * fp32 summation order (the bias is the first addend instead of the last).
+ * min_tiles_per_cta: PER-CALL launch hint (0 = one CTA per SM, the latency optimum): give every CTA at least this
+ * many 128-row tiles, i.e. launch fewer CTAs for the small layers.  Results do not change.  With several batches in
+ * flight the freed SMs run other streams' kernels: +4.5 % scenes/s at 16 on B200 (12 streams), -6 % for one stream. */
+int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_t *idx, const void *G_f16,
                             const float *feat, const float *W0, const float *b0, const float *W0_host,
-                            const float *b0_host, int Cf, float radius, const void *W1_bf16, const float *b1,
-                            const void *W2_bf16, const float *b2, int B, int n, int npoint, int nsample, int C1,
-                            int C2, int C3, float *out, void *out_pm_bf16, void *stream);
+                            const float *b0_host, int Cf, float radius, const void *W1_f16, const float *b1,
+                            const void *W2_f16, const float *b2, int B, int n, int npoint, int nsample, int C1,
+                            int C2, int C3, float *out, void *out_pm_f16, int min_tiles_per_cta, void *stream);
 
-/* ---- point-major (BF16) eval path of the feature-propagation and voting stages ------------------
+/* ---- point-major (FP16) eval path of the feature-propagation and voting stages ------------------
  * These have no C++ counterpart in the reference; each replaces a chain of small ATen launches. */
 
 /* three_nn + inverse-distance weights (pointnet2_modules.py:398-402): idx (B,n,3) bit-identical to
@@ -193,22 +189,22 @@ int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_
 int spc_three_nn_weights(const float *unknown, const float *known, int B, int n, int m, int32_t *idx,
                          float *weight, void *stream);
 
-/* three_interpolate + torch.cat with the skip features (pointnet2_modules.py:404-416), BF16
+/* three_interpolate + torch.cat with the skip features (pointnet2_modules.py:404-416), FP16
  * point-major: known_pm (B,m,C2), skip_pm (B,n,C1) -> X (B,n,C2+C1).  C2, C1 multiples of 8. */
-int spc_interp_cat_pm(const void *known_pm_bf16, const int32_t *idx, const float *weight,
-                      const void *skip_pm_bf16, int B, int n, int m, int C2, int C1, void *X_bf16,
+int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float *weight,
+                      const void *skip_pm_f16, int B, int n, int m, int C2, int C1, void *X_f16,
                       void *stream);
 
 /* Voting tail (models/voting_module.py:52-61 + models/SpaCapNet.py:66-67), vote_factor 1:
  * net (B*S,3+D) f32 = last voting conv WITHOUT bias, point-major; bias (3+D); seed_xyz (B,S,3);
- * seed_pm (B,S,D) BF16 -> vote_xyz (B,S,3), L2-normalised vote features channel-major f32 (B,D,S)
- * and point-major BF16 (B,S,D).  D <= 256. */
-int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz, const void *seed_pm_bf16,
-                  int B, int S, int D, float *vote_xyz, float *vote_feat_cm, void *vote_pm_bf16,
+ * seed_pm (B,S,D) FP16 -> vote_xyz (B,S,3), L2-normalised vote features channel-major f32 (B,D,S)
+ * and point-major FP16 (B,S,D).  D <= 256. */
+int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz, const void *seed_pm_f16,
+                  int B, int S, int D, float *vote_xyz, float *vote_feat_cm, void *vote_pm_f16,
                   void *stream);
 
-/* point-major BF16 (B,n,C) -> channel-major f32 (B,C,n) */
-int spc_pm_to_cm(const void *pm_bf16, int B, int n, int C, float *cm, void *stream);
+/* point-major FP16 (B,n,C) -> channel-major f32 (B,C,n) */
+int spc_pm_to_cm(const void *pm_f16, int B, int n, int C, float *cm, void *stream);
 
 /* ---- training-mode BatchNorm + ReLU of a shared-MLP block -------------------------------------------
  * Replaces nn.BatchNorm2d(training) + nn.ReLU(inplace=True) of the reference's Conv2d block

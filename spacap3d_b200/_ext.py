@@ -7,9 +7,16 @@ Differences, all invisible to callers: outputs are allocated with torch.empty (e
 written by the kernels), launches go to torch's *current* stream under a device guard taken from
 the input tensor, and a failed launch raises instead of calling exit(-1).
 """
+import threading
+
 import torch
 
 from . import _lib
+
+# 16-bit storage type of the eval fast paths (fused SA operands, point-major activations).  fp16, not bf16: 11
+# significant bits instead of 8 at the same tensor-core rate, ~8x closer to the fp32 reference; the kernels saturate
+# at +-65504 instead of overflowing (csrc/sa_fused.cu).
+HALF = torch.float16
 
 
 def _check(t, name, dtype):
@@ -37,9 +44,42 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-# clouds at least this large get a workspace, which lets the library use its Morton-sorted, culled
-# FPS kernel (fps.cu); the result is identical either way
-FPS_WORKSPACE_MIN_N = 8192
+# clouds at least this large get a workspace, which lets the library use its bucketed FPS kernel
+# (fps.cu); the result is identical either way
+FPS_WORKSPACE_MIN_N = 4096
+
+FPS_AUTO, FPS_CLUSTER, FPS_BUCKET = 0, 1, 2      # include/spacap3d_ops.h SPC_FPS_*
+
+
+class _LaunchOptions(threading.local):
+    """Per-THREAD launch hints handed to the library with every call (the C ABI keeps no mutable state, so that
+    nn.DataParallel worker threads / several pipelines in one process cannot disturb each other).  None of them
+    changes results."""
+    fps_algo = FPS_AUTO        # sampler selection for large clouds
+    sa_min_tiles = 0           # fused SA kernel: at least this many 128-row tiles per CTA (0 = one CTA per SM)
+
+
+_options = _LaunchOptions()
+
+
+class launch_options:
+    """Context manager: `with launch_options(sa_min_tiles=16): ...` (thread-local, re-entrant)."""
+
+    def __init__(self, **kw):
+        for k in kw:
+            if not hasattr(_LaunchOptions, k):
+                raise TypeError("unknown launch option %r" % k)
+        self.kw = kw
+
+    def __enter__(self):
+        self.saved = {k: getattr(_options, k) for k in self.kw}
+        for k, v in self.kw.items():
+            setattr(_options, k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            setattr(_options, k, v)
 
 
 def furthest_point_sampling(points, nsamples):
@@ -52,8 +92,8 @@ def furthest_point_sampling(points, nsamples):
         if N >= FPS_WORKSPACE_MIN_N and nsamples >= 2:
             nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
-            _lib.call("spc_furthest_point_sampling_ex", points.data_ptr(), B, N, int(nsamples),
-                      out.data_ptr(), None, 0, ws.data_ptr(), nbytes, _stream())
+            _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), None, 0, None, None, ws.data_ptr(), nbytes, int(_options.fps_algo), _stream())
         else:
             _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), None, _stream())
@@ -88,15 +128,16 @@ def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False, known
             _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples), out.data_ptr(),
                       new_xyz.data_ptr(), int(bool(hint_ordered) and 2 <= nsamples <= N),
                       known_ordered.data_ptr() if known_ordered is not None else None,
-                      strict.data_ptr() if strict is not None else None, ws.data_ptr(), nbytes, _stream())
+                      strict.data_ptr() if strict is not None else None, ws.data_ptr(), nbytes,
+                      int(_options.fps_algo), _stream())
         return (out, new_xyz, strict) if want_strict else (out, new_xyz)
     with torch.cuda.device(points.device):
         if (hint_ordered and 2 <= nsamples <= N) or (N >= FPS_WORKSPACE_MIN_N and nsamples >= 2):
             nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
-            _lib.call("spc_furthest_point_sampling_ex", points.data_ptr(), B, N, int(nsamples),
-                      out.data_ptr(), new_xyz.data_ptr(), int(bool(hint_ordered)), ws.data_ptr(), nbytes,
-                      _stream())
+            _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples),
+                      out.data_ptr(), new_xyz.data_ptr(), int(bool(hint_ordered)), None, None, ws.data_ptr(), nbytes,
+                      int(_options.fps_algo), _stream())
         else:
             _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), new_xyz.data_ptr(), _stream())
@@ -232,8 +273,8 @@ def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=
     """Fused set-abstraction forward (eval): gather + layer 0 + two tcgen05 1x1 convs + max-pool.
     See spc_sa_fused_forward in include/spacap3d_ops.h.
       in-line form   : G is None, feat (B,Cf,n) or None, W0 (C1,3+Cf)
-      projected form : G (B,n,C1) bf16 = per-point projection of the features, W0 (C1,3)
-    Returns out (B,C3,npoint) f32, and also the point-major bf16 copy (B,npoint,C3) when
+      projected form : G (B,n,C1) fp16 = per-point projection of the features, W0 (C1,3)
+    Returns out (B,C3,npoint) f32, and also the point-major fp16 copy (B,npoint,C3) when
     want_point_major.  Raises _lib.SpcUnsupported when the library has no kernel for the shape
     (the caller then uses the unfused CUDA ops)."""
     _check(xyz, "xyz", torch.float32)
@@ -241,8 +282,8 @@ def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=
     _check(idx, "idx", torch.int32)
     _check(W0, "W0", torch.float32)
     _check(b0, "b0", torch.float32)
-    _check(W1, "W1", torch.bfloat16)
-    _check(W2, "W2", torch.bfloat16)
+    _check(W1, "W1", HALF)
+    _check(W2, "W2", HALF)
     _check(b1, "b1", torch.float32)
     _check(b2, "b2", torch.float32)
     _same_device(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2)
@@ -253,7 +294,7 @@ def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=
     assert W2.shape[1] == C2 and b1.numel() == C2 and b2.numel() == C3 and b0.numel() == C1
     Cf, pG, pfeat = 0, None, None
     if G is not None:
-        _check(G, "G", torch.bfloat16)
+        _check(G, "G", HALF)
         _same_device(xyz, G)
         assert G.shape == (B, n, C1) and W0.shape == (C1, 3)
         pG = G.data_ptr()
@@ -272,12 +313,13 @@ def sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, *, G=None, feat=
         assert W0_host.shape == W0.shape and b0_host.numel() == C1
         pW0h, pb0h = W0_host.data_ptr(), b0_host.data_ptr()
     out = torch.empty((B, C3, npoint), dtype=torch.float32, device=xyz.device)
-    out_pm = torch.empty((B, npoint, C3), dtype=torch.bfloat16, device=xyz.device) if want_point_major else None
+    out_pm = torch.empty((B, npoint, C3), dtype=HALF, device=xyz.device) if want_point_major else None
     with torch.cuda.device(xyz.device):
         _lib.call("spc_sa_fused_forward_ex", xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(),
                   pG, pfeat, W0.data_ptr(), b0.data_ptr(), pW0h, pb0h, int(Cf), float(radius), W1.data_ptr(),
                   b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), B, n, npoint, nsample, C1, C2, C3,
-                  out.data_ptr(), out_pm.data_ptr() if out_pm is not None else None, _stream())
+                  out.data_ptr(), out_pm.data_ptr() if out_pm is not None else None, int(_options.sa_min_tiles),
+                  _stream())
     return (out, out_pm) if want_point_major else out
 
 
@@ -298,15 +340,15 @@ def three_nn_weights(unknown, known):
 
 
 def interp_cat_pm(known_pm, idx, weight, skip_pm):
-    """Point-major bf16: X (B,n,C2+C1) = [3-NN interpolation of known_pm (B,m,C2), skip_pm (B,n,C1)]."""
-    _check(known_pm, "known_pm", torch.bfloat16)
+    """Point-major fp16: X (B,n,C2+C1) = [3-NN interpolation of known_pm (B,m,C2), skip_pm (B,n,C1)]."""
+    _check(known_pm, "known_pm", HALF)
     _check(idx, "idx", torch.int32)
     _check(weight, "weight", torch.float32)
-    _check(skip_pm, "skip_pm", torch.bfloat16)
+    _check(skip_pm, "skip_pm", HALF)
     _same_device(known_pm, idx, weight, skip_pm)
     B, m, C2 = known_pm.shape
     n, C1 = skip_pm.shape[1], skip_pm.shape[2]
-    X = torch.empty((B, n, C2 + C1), dtype=torch.bfloat16, device=known_pm.device)
+    X = torch.empty((B, n, C2 + C1), dtype=HALF, device=known_pm.device)
     with torch.cuda.device(known_pm.device):
         _lib.call("spc_interp_cat_pm", known_pm.data_ptr(), idx.data_ptr(), weight.data_ptr(), skip_pm.data_ptr(),
                   B, n, m, C2, C1, X.data_ptr(), _stream())
@@ -314,18 +356,18 @@ def interp_cat_pm(known_pm, idx, weight, skip_pm):
 
 
 def vote_tail(net, bias, seed_xyz, seed_pm):
-    """Voting tail: net (B*S,3+D) f32 (no bias), bias (3+D), seed_xyz (B,S,3), seed_pm (B,S,D) bf16 ->
-    vote_xyz (B,S,3), vote features L2-normalised: channel-major f32 (B,D,S) and point-major bf16 (B,S,D)."""
+    """Voting tail: net (B*S,3+D) f32 (no bias), bias (3+D), seed_xyz (B,S,3), seed_pm (B,S,D) fp16 ->
+    vote_xyz (B,S,3), vote features L2-normalised: channel-major f32 (B,D,S) and point-major fp16 (B,S,D)."""
     _check(net, "net", torch.float32)
     _check(bias, "bias", torch.float32)
     _check(seed_xyz, "seed_xyz", torch.float32)
-    _check(seed_pm, "seed_pm", torch.bfloat16)
+    _check(seed_pm, "seed_pm", HALF)
     _same_device(net, bias, seed_xyz, seed_pm)
     B, S, D = seed_pm.shape
     assert net.shape == (B * S, 3 + D) and bias.numel() == 3 + D
     vote_xyz = torch.empty((B, S, 3), dtype=torch.float32, device=net.device)
     cm = torch.empty((B, D, S), dtype=torch.float32, device=net.device)
-    pm = torch.empty((B, S, D), dtype=torch.bfloat16, device=net.device)
+    pm = torch.empty((B, S, D), dtype=HALF, device=net.device)
     with torch.cuda.device(net.device):
         _lib.call("spc_vote_tail", net.data_ptr(), bias.data_ptr(), seed_xyz.data_ptr(), seed_pm.data_ptr(), B, S, D,
                   vote_xyz.data_ptr(), cm.data_ptr(), pm.data_ptr(), _stream())
@@ -333,8 +375,8 @@ def vote_tail(net, bias, seed_xyz, seed_pm):
 
 
 def pm_to_cm(pm):
-    """(B,n,C) bf16 point-major -> (B,C,n) f32 channel-major."""
-    _check(pm, "pm", torch.bfloat16)
+    """(B,n,C) fp16 point-major -> (B,C,n) f32 channel-major."""
+    _check(pm, "pm", HALF)
     _same_device(pm)
     B, n, C = pm.shape
     cm = torch.empty((B, C, n), dtype=torch.float32, device=pm.device)

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -19,10 +19,7 @@ _f = ctypes.c_float
 SIGNATURES = {
     "spc_furthest_point_sampling": [_p, _i, _i, _i, _p, _p, _p],
     "spc_furthest_point_sampling_ex": [_p, _i, _i, _i, _p, _p, _i, _p, ctypes.c_size_t, _p],
-    "spc_furthest_point_sampling_ex2": [_p, _i, _i, _i, _p, _p, _i, _p, _p, _p, ctypes.c_size_t, _p],
-    "spc_set_fps_cluster": [_i],
-    "spc_set_fps_cull": [_i],
-    "spc_set_sa_min_tiles": [_i],
+    "spc_furthest_point_sampling_ex2": [_p, _i, _i, _i, _p, _p, _i, _p, _p, _p, ctypes.c_size_t, _i, _p],
     "spc_gather_points": [_p, _p, _i, _i, _i, _i, _p, _p],
     "spc_gather_points_grad": [_p, _p, _i, _i, _i, _i, _p, _p],
     "spc_ball_query": [_p, _p, _i, _i, _i, _f, _i, _p, _p],
@@ -52,7 +49,7 @@ SIGNATURES = {
     "spc_sa_fused_forward": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,
                              _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "spc_sa_fused_forward_ex": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,
-                                _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+                                _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
 }
 
 _lib = None

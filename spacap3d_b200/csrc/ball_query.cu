@@ -345,7 +345,7 @@ extern "C" int spc_ball_query_ex(const float *new_xyz, const float *xyz, int B, 
   // the grid pays off once the all-pairs scan dominates; tiny clouds stay on the brute-force kernel
   const bool use_grid = workspace && workspace_bytes >= spc_ball_query_workspace_bytes(B, N) &&
                         N >= 1024 && (long long)N * M >= (1LL << 19) && nsample <= 1024 && B <= 65535 &&
-                        radius > 0.f && !getenv("SPC_BQ_BRUTE");
+                        radius > 0.f;
   if (!use_grid) return ball_query_brute(new_xyz, xyz, B, N, M, radius, nsample, idx, stream_);
   cudaStream_t stream = (cudaStream_t)stream_;
   uintptr_t base = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;

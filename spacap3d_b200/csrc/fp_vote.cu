@@ -1,8 +1,8 @@
-// fp_vote.cu -- small fused kernels around the point-major (bf16) eval path of the detector's
+// fp_vote.cu -- small fused kernels around the point-major (fp16) eval path of the detector's
 // feature-propagation and voting stages.  They replace chains of tiny
 // ATen launches (sqrt/add/reciprocal/sum/div, cat, transpose copies, norm/div; ~18 % of the SM time
 // of a forward, profiles/r1_sm_cycles_per_kernel_one_forward.csv) with one kernel each.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -84,18 +84,18 @@ __global__ void __launch_bounds__(NW_THREADS) three_nn_weights_kernel(const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-// three_interpolate + concat with the skip features, point-major bf16 in and out:
+// three_interpolate + concat with the skip features, point-major fp16 in and out:
 //   X[b, j, 0:C2]      = sum_t w[b,j,t] * known_pm[b, idx[b,j,t], :]     (fp32 accumulate)
 //   X[b, j, C2:C2+C1]  = skip_pm[b, j, :]
 // (reference: three_interpolate + torch.cat, pointnet2_modules.py:404-416, there on (B,C,n) fp32).
 // One warp per point; lanes stride over 8-channel (16-byte) chunks => coalesced rows.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __nv_bfloat16 *__restrict__ known_pm,
+__global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __half *__restrict__ known_pm,
                                                             const int32_t *__restrict__ idx,
                                                             const float *__restrict__ weight,
-                                                            const __nv_bfloat16 *__restrict__ skip_pm, int n,
+                                                            const __half *__restrict__ skip_pm, int n,
                                                             int m, int C2, int C1,
-                                                            __nv_bfloat16 *__restrict__ X) {
+                                                            __half *__restrict__ X) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -114,11 +114,14 @@ __global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __nv_bfloat16 
     uint32_t o[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      // same contraction order as three_interpolate: fma(p3,w3, fma(p1,w1, p2*w2))
-      const float lo = fmaf(__uint_as_float(p3[q] << 16), w3, fmaf(__uint_as_float(p1[q] << 16), w1, __uint_as_float(p2[q] << 16) * w2));
-      const float hi = fmaf(__uint_as_float(p3[q] & 0xffff0000u), w3,
-                            fmaf(__uint_as_float(p1[q] & 0xffff0000u), w1, __uint_as_float(p2[q] & 0xffff0000u) * w2));
-      __nv_bfloat162 pk = __floats2bfloat162_rn(lo, hi);
+      // same contraction order as three_interpolate: fma(p3,w3, fma(p1,w1, p2*w2)); a convex combination of
+      // fp16 values cannot leave the fp16 range
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2 *>(&p1[q]));
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&p2[q]));
+      const float2 f3 = __half22float2(*reinterpret_cast<const __half2 *>(&p3[q]));
+      const float lo = fmaf(f3.x, w3, fmaf(f1.x, w1, f2.x * w2));
+      const float hi = fmaf(f3.y, w3, fmaf(f1.y, w1, f2.y * w2));
+      __half2 pk = __floats2half2_rn(lo, hi);
       o[q] = *reinterpret_cast<uint32_t *>(&pk);
     }
     out[c] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __nv_bfloat16 
 //   vote_xyz[b,s,:]      = seed_xyz[b,s,:] + net[.,0:3] + bias[0:3]
 //   v                    = seed_feat[b,s,:] + net[.,3:] + bias[3:]
 //   vote_features[b,:,s] = v / ||v||_2          (channel-major fp32, the tensor the reference exposes)
-//   vote_pm[b,s,:]       = same, point-major bf16 (input of the vote-aggregation projection GEMM)
+//   vote_pm[b,s,:]       = same, point-major fp16 (input of the vote-aggregation projection GEMM)
 // One CTA per 32 seeds: a warp normalises one seed at a time (lanes over channels), the tile is
 // transposed through shared memory so that the channel-major store is coalesced along seeds.
 // ------------------------------------------------------------------------------------------------
@@ -141,10 +144,10 @@ constexpr int VT_SEEDS = 32;
 
 __global__ void __launch_bounds__(256) vote_tail_kernel(const float *__restrict__ net, const float *__restrict__ bias,
                                                         const float *__restrict__ seed_xyz,
-                                                        const __nv_bfloat16 *__restrict__ seed_pm, int S, int D,
+                                                        const __half *__restrict__ seed_pm, int S, int D,
                                                         float *__restrict__ vote_xyz,
                                                         float *__restrict__ vote_feat_cm,
-                                                        __nv_bfloat16 *__restrict__ vote_pm) {
+                                                        __half *__restrict__ vote_pm) {
   extern __shared__ float s_tile[];                  // [D][VT_SEEDS + 1]
   const int b = blockIdx.y;
   const int s0 = blockIdx.x * VT_SEEDS;
@@ -156,26 +159,26 @@ __global__ void __launch_bounds__(256) vote_tail_kernel(const float *__restrict_
     const float *row = net + ((size_t)b * S + s) * ld;
     if (lane < 3)
       vote_xyz[((size_t)b * S + s) * 3 + lane] = __ldg(seed_xyz + ((size_t)b * S + s) * 3 + lane) + __ldg(row + lane) + __ldg(bias + lane);
-    const __nv_bfloat16 *sf = seed_pm + ((size_t)b * S + s) * D;
+    const __half *sf = seed_pm + ((size_t)b * S + s) * D;
     float v[8];                                      // D <= 256: channel c = lane + 32*i
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
-      v[i] = c < D ? __bfloat162float(sf[c]) + __ldg(row + 3 + c) + __ldg(bias + 3 + c) : 0.f;
+      v[i] = c < D ? __half2float(sf[c]) + __ldg(row + 3 + c) + __ldg(bias + 3 + c) : 0.f;
       ss = fmaf(v[i], v[i], ss);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float inv = 1.0f / sqrtf(ss);
-    __nv_bfloat16 *op = vote_pm + ((size_t)b * S + s) * D;
+    __half *op = vote_pm + ((size_t)b * S + s) * D;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
       if (c < D) {
         const float r = v[i] * inv;
         s_tile[c * (VT_SEEDS + 1) + t] = r;
-        op[c] = __float2bfloat16_rn(r);
+        op[c] = __float2half_rn(r);
       }
     }
   }
@@ -187,8 +190,8 @@ __global__ void __launch_bounds__(256) vote_tail_kernel(const float *__restrict_
   }
 }
 
-// point-major bf16 (B,n,C) -> channel-major fp32 (B,C,n)   (tile transpose through shared memory)
-__global__ void __launch_bounds__(256) pm_to_cm_kernel(const __nv_bfloat16 *__restrict__ pm, int n, int C,
+// point-major fp16 (B,n,C) -> channel-major fp32 (B,C,n)   (tile transpose through shared memory)
+__global__ void __launch_bounds__(256) pm_to_cm_kernel(const __half *__restrict__ pm, int n, int C,
                                                        float *__restrict__ cm) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256) pm_to_cm_kernel(const __nv_bfloat16 *__re
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     const int p = p0 + r, c = c0 + tx;
-    t[r][tx] = (p < n && c < C) ? __bfloat162float(pm[((size_t)b * n + p) * C + c]) : 0.f;
+    t[r][tx] = (p < n && c < C) ? __half2float(pm[((size_t)b * n + p) * C + c]) : 0.f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
@@ -221,43 +224,43 @@ extern "C" int spc_three_nn_weights(const float *unknown, const float *known, in
   return SPC_OK;
 }
 
-extern "C" int spc_interp_cat_pm(const void *known_pm_bf16, const int32_t *idx, const float *weight,
-                                 const void *skip_pm_bf16, int B, int n, int m, int C2, int C1,
-                                 void *X_bf16, void *stream_) {
+extern "C" int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float *weight,
+                                 const void *skip_pm_f16, int B, int n, int m, int C2, int C1,
+                                 void *X_f16, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && n >= 0 && m >= 1 && C2 >= 8 && C1 >= 0, "interp_cat_pm: bad sizes");
   SPC_CHECK_ARG(C2 % 8 == 0 && C1 % 8 == 0, "interp_cat_pm: channel counts must be multiples of 8");
   if (B == 0 || n == 0) return SPC_OK;
-  SPC_CHECK_ARG(known_pm_bf16 && idx && weight && X_bf16 && (skip_pm_bf16 || C1 == 0), "interp_cat_pm: null pointer");
+  SPC_CHECK_ARG(known_pm_f16 && idx && weight && X_f16 && (skip_pm_f16 || C1 == 0), "interp_cat_pm: null pointer");
   SPC_CHECK_ARG(B <= 65535, "interp_cat_pm: B too large");
   interp_cat_pm_kernel<<<dim3(ceil_div(n, 8), B), 256, 0, (cudaStream_t)stream_>>>(
-      (const __nv_bfloat16 *)known_pm_bf16, idx, weight, (const __nv_bfloat16 *)skip_pm_bf16, n, m, C2, C1,
-      (__nv_bfloat16 *)X_bf16);
+      (const __half *)known_pm_f16, idx, weight, (const __half *)skip_pm_f16, n, m, C2, C1,
+      (__half *)X_f16);
   SPC_LAUNCH_CHECK("interp_cat_pm_kernel");
   return SPC_OK;
 }
 
 extern "C" int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz,
-                             const void *seed_pm_bf16, int B, int S, int D, float *vote_xyz,
-                             float *vote_feat_cm, void *vote_pm_bf16, void *stream_) {
+                             const void *seed_pm_f16, int B, int S, int D, float *vote_xyz,
+                             float *vote_feat_cm, void *vote_pm_f16, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && S >= 0 && D >= 1 && D <= 256, "vote_tail: feature dim must be in 1..256");
   if (B == 0 || S == 0) return SPC_OK;
-  SPC_CHECK_ARG(net && bias && seed_xyz && seed_pm_bf16 && vote_xyz && vote_feat_cm && vote_pm_bf16, "vote_tail: null pointer");
+  SPC_CHECK_ARG(net && bias && seed_xyz && seed_pm_f16 && vote_xyz && vote_feat_cm && vote_pm_f16, "vote_tail: null pointer");
   SPC_CHECK_ARG(B <= 65535, "vote_tail: B too large");
   const size_t smem = (size_t)D * (VT_SEEDS + 1) * sizeof(float);
   vote_tail_kernel<<<dim3(ceil_div(S, VT_SEEDS), B), 256, smem, (cudaStream_t)stream_>>>(
-      net, bias, seed_xyz, (const __nv_bfloat16 *)seed_pm_bf16, S, D, vote_xyz, vote_feat_cm,
-      (__nv_bfloat16 *)vote_pm_bf16);
+      net, bias, seed_xyz, (const __half *)seed_pm_f16, S, D, vote_xyz, vote_feat_cm,
+      (__half *)vote_pm_f16);
   SPC_LAUNCH_CHECK("vote_tail_kernel");
   return SPC_OK;
 }
 
-extern "C" int spc_pm_to_cm(const void *pm_bf16, int B, int n, int C, float *cm, void *stream_) {
+extern "C" int spc_pm_to_cm(const void *pm_f16, int B, int n, int C, float *cm, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && n >= 0 && C >= 0, "pm_to_cm: bad sizes");
   if (B == 0 || n == 0 || C == 0) return SPC_OK;
-  SPC_CHECK_ARG(pm_bf16 && cm, "pm_to_cm: null pointer");
+  SPC_CHECK_ARG(pm_f16 && cm, "pm_to_cm: null pointer");
   SPC_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "pm_to_cm: B or C too large");
   pm_to_cm_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32), B), 256, 0, (cudaStream_t)stream_>>>(
-      (const __nv_bfloat16 *)pm_bf16, n, C, cm);
+      (const __half *)pm_f16, n, C, cm);
   SPC_LAUNCH_CHECK("pm_to_cm_kernel");
   return SPC_OK;
 }

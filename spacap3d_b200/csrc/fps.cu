@@ -24,6 +24,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -279,20 +281,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
 }
 
 // ================================================================================================
-// Culled variant for large clouds.
-//
-// After the first few dozen picks a new centre only changes the min-distance of points within the
-// current sampling radius, i.e. of a few per cent of the cloud -- yet the kernel above updates
-// every point every round, and that distance math is 2/3 of its issue slots (which is what limits
-// throughput once several scenes share an SM).  Here the points are first sorted along a Morton
-// curve (fps_morton_sort_kernel), so that the 32*P points of a WARP are spatially compact; each
-// warp keeps the bounding box of its points and its current best candidate.  If the new centre is
-// farther from the box than the warp's largest min-distance, no min-distance in the warp can
-// change (d >= box distance >= every t) and the warp just republishes its cached candidate.
-// The test is conservative w.r.t. fp32 rounding (factor 1-1e-5), so the result is bit-identical.
-// Because points are no longer laid out in the reference's tie-break order, ties are broken
-// explicitly with the virtual index v (one extra redux per level); each thread's slots are sorted
-// by v once at load time so that the strict '>' scan still keeps the lowest v.
+// Morton sort (prepass of the bucketed sampler below): spatially compact runs of consecutive points.
 // ================================================================================================
 constexpr int FMS_THREADS = 1024;
 constexpr int FMS_BINS = 32768;       // 32^3 Morton cells
@@ -407,18 +396,6 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
   }
 }
 
-struct __align__(16) FpsCandV {
-  unsigned key, v; int k; float x;
-  float y, z; unsigned pad[2];
-};
-
-__device__ __forceinline__ void st_async_v2(uint32_t remote_addr, uint32_t a, uint32_t b, uint32_t remote_bar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::
-                   "r"(remote_addr),
-               "r"(a), "r"(b), "r"(remote_bar)
-               : "memory");
-}
-
 // Several lanes hold the maximal key: the smallest virtual index wins.  Deliberately NOT inlined: ptxas
 // otherwise if-converts the rare path into predicated redux that sit on every round's dependency chain.
 __device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned lane) {
@@ -426,310 +403,235 @@ __device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned 
   return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
 }
 
-// XYZ_SMEM = false: coordinates and min-distances in registers (128 regs, 100 KB smem: two CTAs per SM).
-// XYZ_SMEM = true : only the min-distances stay in registers; coordinates are read from shared memory by
-//   the (few) warps that are not culled, point indices are kept as uint16 and the tie-break index is
-//   recomputed from them => <= 80 regs and 70 KB smem: THREE CTAs per SM, i.e. a scene occupies 2.7 SMs
-//   instead of 4 for the duration of the call.
-// TRACK = true additionally maintains p.strict_out (see below); compiled out otherwise (it costs registers).
-template <int P, int THREADS, bool XYZ_SMEM, bool TRACK>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (XYZ_SMEM ? 3 : 2) : 1))
-fps_cull_kernel(const FpsParams p, const int32_t *__restrict__ perm_all) {
-  constexpr int NW = THREADS / 32;
-  extern __shared__ float s_xyz[];  // [3][P][THREADS] xyz + ([P][THREADS] k + [P][THREADS] v | [P][THREADS] k16)
-  float *sx = s_xyz, *sy = s_xyz + P * THREADS, *sz = s_xyz + 2 * P * THREADS;
-  // during the load-time sort the XYZ_SMEM variant borrows the (not yet written) x / y planes for v / k
-  int *sk = XYZ_SMEM ? reinterpret_cast<int *>(sy) : reinterpret_cast<int *>(s_xyz + 3 * P * THREADS);
-  unsigned *sv = XYZ_SMEM ? reinterpret_cast<unsigned *>(sx) : reinterpret_cast<unsigned *>(s_xyz + 4 * P * THREADS);
-  uint16_t *sk16 = reinterpret_cast<uint16_t *>(s_xyz + 3 * P * THREADS);
-  auto v_of_k = [&](unsigned k) -> unsigned {
-    const unsigned res = p.log2T ? (__brev(k & (unsigned)(p.T - 1)) >> (32 - p.log2T)) : 0u;
-    return res * (unsigned)p.Q + (k >> p.log2T);      // T is a power of two
-  };
-  __shared__ FpsCandV w_cand[2][NW];
-  __shared__ FpsCandV c_cand[2][kMaxCluster];
-  __shared__ __align__(8) uint64_t c_bar[2];
+// ================================================================================================
+// Bucketed sampler: ONE small CTA per scene, points parked in L2.
+//
+// What limits detector throughput is not how long one sampling call takes but how much of the GPU it
+// holds while it runs: the kernels above keep every point of a scene on-chip, which pins 2.7-4 SMs
+// per 40 k-point scene for the whole 1.3-1.5 ms (60 % of all SM time of a forward in round 1).  Yet after
+// the first few dozen picks a new centre changes the min-distance of a few dozen points only.
+//
+// Here the Morton-sorted points live in GLOBAL memory as float4 (x, y, z, running min-distance) -- 640 KB per
+// 40 k-point scene, L2-resident -- cut into buckets of BS consecutive points.  The CTA keeps per bucket, in
+// shared memory (48 B): the bounding box of its selectable points and its current best candidate
+// (key = min-distance bits + 1, tie-break index v, point index, coordinates).  A round is
+//   1. cull   : every thread tests 2-3 buckets: can the new centre lower any min-distance in it?
+//               (box distance^2 * (1 - 1e-5) >= the bucket's largest min-distance => provably not); the
+//               touched buckets (a handful once ~100 centres exist) are appended to a list;
+//   2. update : one warp per touched bucket loads its BS points from L2 (the only global access on the
+//               round's dependency chain: ~250 cycles, the same as the DSMEM exchange of the cluster kernel),
+//               updates the min-distances, stores the changed ones, and re-derives the bucket's candidate;
+//   3. select : arg-max over the bucket candidates (threads scan 2-3 records each, two redux levels).
+// No cluster, no DSMEM, three bar.sync per round; 256 threads and ~32 KB of shared memory, so FOUR scenes
+// share an SM.  Same arithmetic as everywhere else (sqdist_ref, fminf, strict tie-break on the reference's
+// virtual index), so the picks are bit-identical.
+// ================================================================================================
+constexpr int FB_THREADS = 256;
+constexpr unsigned FB_KEY_INIT = 0x501502F9u + 1u;      // __float_as_uint(1e10f) + 1
 
-  cg::cluster_group cluster = cg::this_cluster();
-  const unsigned C = cluster.num_blocks();
-  const unsigned rank = cluster.block_rank();
+__device__ __forceinline__ unsigned fb_v_of_k(unsigned k, int T, int log2T, int Q) {
+  const unsigned res = log2T ? (__brev(k & (unsigned)(T - 1)) >> (32 - log2T)) : 0u;
+  return res * (unsigned)Q + (k >> log2T);      // T is a power of two
+}
+
+// warp per bucket: gather the Morton-sorted points into (x, y, z, t0), t0 = 1e10 or -1 for points the reference
+// never selects (|p|^2 <= 1e-3, F5) and for the padding; bounding box of the selectable points.
+template <int BS>
+__global__ void __launch_bounds__(256) fps_bucket_build_kernel(const float *__restrict__ xyz_all,
+                                                               const int32_t *__restrict__ perm_all, int N, int NB,
+                                                               float4 *__restrict__ pts_all,
+                                                               int32_t *__restrict__ kk_all,
+                                                               float *__restrict__ boxes_all) {
   const int scene = blockIdx.y;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= NB) return;
+  const float *xyz = xyz_all + (size_t)scene * N * 3;
+  const int32_t *perm = perm_all + (size_t)scene * N;
+  float4 *pts = pts_all + (size_t)scene * NB * BS;
+  int32_t *kk = kk_all + (size_t)scene * NB * BS;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+  for (int u = 0; u < BS / 32; ++u) {
+    const int q = b * BS + u * 32 + lane;
+    float4 v = make_float4(0.f, 0.f, 0.f, -1.0f);
+    int k = 0;
+    if (q < N) {
+      k = __ldg(perm + q);
+      v.x = __ldg(xyz + 3 * k + 0);
+      v.y = __ldg(xyz + 3 * k + 1);
+      v.z = __ldg(xyz + 3 * k + 2);
+      const float mag = __fmaf_rn(v.z, v.z, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y)));
+      v.w = ((double)mag <= 1e-3) ? -1.0f : 1e10f;   // reference compares in double (F5)
+      if (v.w > 0.f) {
+        lo[0] = fminf(lo[0], v.x); lo[1] = fminf(lo[1], v.y); lo[2] = fminf(lo[2], v.z);
+        hi[0] = fmaxf(hi[0], v.x); hi[1] = fmaxf(hi[1], v.y); hi[2] = fmaxf(hi[2], v.z);
+      }
+    }
+    pts[q] = v;
+    kk[q] = k;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+  }
+  if (lane < 6) boxes_all[((size_t)scene * NB + b) * 6 + lane] = lane < 3 ? lo[lane] : hi[lane - 3];
+}
+
+template <int BS, int U>
+__global__ void __launch_bounds__(FB_THREADS, 4)
+fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict__ kk_all,
+                  const float *__restrict__ boxes_all, int NB) {
+  constexpr int NW = FB_THREADS / 32;
+  constexpr int PPL = BS / 32;                        // points per lane and bucket
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  float4 *s_kxyz = reinterpret_cast<float4 *>(fb_smem);            // [NB] candidate: (k bits, x, y, z)
+  float4 *s_box4 = s_kxyz + NB;                                    // [NB] (lox, loy, loz, hix)
+  float2 *s_box2 = reinterpret_cast<float2 *>(s_box4 + NB);        // [NB] (hiy, hiz)
+  uint2 *s_keyv = reinterpret_cast<uint2 *>(s_box2 + NB);          // [NB] candidate: (key, v); key 0 = nothing selectable
+  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_keyv + NB);    // [NB] touched buckets of the round
+  __shared__ uint4 s_wc[NW];                                       // per-warp (key, v, bucket)
+  __shared__ int s_cnt;
+
+  const int scene = blockIdx.x;
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31u, warp = tid >> 5;
   const float *xyz = p.xyz + (size_t)scene * p.N * 3;
-  const int32_t *perm = perm_all + (size_t)scene * p.N;
-  const unsigned g = rank * THREADS + tid;
-  const unsigned q0 = g * P;                    // first Morton-sorted position owned by this thread
-  if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {   // verified shortcut, as in fps_cluster_kernel
-    if (g == 0 && p.strict_out) p.strict_out[scene] = 1;       // the proof implies strict unique maxima
+  if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {       // verified shortcut, as in fps_cluster_kernel
+    if (tid == 0 && p.strict_out) p.strict_out[scene] = 1;
     int32_t *oidx = p.idx + (size_t)scene * p.npoint;
-    for (unsigned j = g; j < (unsigned)p.npoint; j += C * THREADS) oidx[j] = (int)j;
+    for (int j = tid; j < p.npoint; j += FB_THREADS) oidx[j] = j;
     if (p.new_xyz) {
       float *o = p.new_xyz + (size_t)scene * p.npoint * 3;
-      for (unsigned e = g; e < 3u * (unsigned)p.npoint; e += C * THREADS) o[e] = __ldg(xyz + e);
+      for (int e = tid; e < 3 * p.npoint; e += FB_THREADS) o[e] = __ldg(xyz + e);
     }
     return;
   }
-
-  // ---- load: (v, k) of my slots into smem, insertion-sort them by v, then fetch the coordinates ---
-  int nvalid = 0;
-  for (int s = 0; s < P; ++s) {
-    const unsigned q = q0 + s;
-    unsigned v = 0xffffffffu;
-    int k = 0;
-    if (q < (unsigned)p.N) {
-      k = __ldg(perm + q);
-      v = v_of_k((unsigned)k);
-      ++nvalid;
-    }
-    int pos = s;                                                 // insertion sort (ascending v)
-    while (pos > 0 && sv[(pos - 1) * THREADS + tid] > v) {
-      sv[pos * THREADS + tid] = sv[(pos - 1) * THREADS + tid];
-      sk[pos * THREADS + tid] = sk[(pos - 1) * THREADS + tid];
-      --pos;
-    }
-    sv[pos * THREADS + tid] = v;
-    sk[pos * THREADS + tid] = k;
+  float4 *pts = pts_all + (size_t)scene * NB * BS;
+  const int32_t *kk = kk_all + (size_t)scene * NB * BS;
+  const float *boxes = boxes_all + (size_t)scene * NB * 6;
+  for (int b = tid; b < NB; b += FB_THREADS) {
+    const float lx = __ldg(boxes + 6 * b + 0), ly = __ldg(boxes + 6 * b + 1), lz = __ldg(boxes + 6 * b + 2);
+    const float hx = __ldg(boxes + 6 * b + 3), hy = __ldg(boxes + 6 * b + 4), hz = __ldg(boxes + 6 * b + 5);
+    s_box4[b] = make_float4(lx, ly, lz, hx);
+    s_box2[b] = make_float2(hy, hz);
+    s_keyv[b] = make_uint2(hx >= lx ? FB_KEY_INIT : 0u, 0xffffffffu);   // every min-distance starts at 1e10
+    s_kxyz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  float x[P], y[P], z[P], t[P];
-  int kk[P];
-#pragma unroll
-  for (int s = 0; s < P; ++s) kk[s] = sk[s * THREADS + tid];   // before the planes are overwritten
-  float lox = INFINITY, loy = INFINITY, loz = INFINITY, hix = -INFINITY, hiy = -INFINITY, hiz = -INFINITY;
-#pragma unroll
-  for (int s = 0; s < P; ++s) {
-    float px = 0.f, py = 0.f, pz = 0.f, pt = -1.0f;
-    if (s < nvalid) {
-      const int k = kk[s];
-      px = __ldg(xyz + 3 * k + 0);
-      py = __ldg(xyz + 3 * k + 1);
-      pz = __ldg(xyz + 3 * k + 2);
-      const float mag = __fmaf_rn(pz, pz, __fmaf_rn(px, px, __fmul_rn(py, py)));
-      pt = ((double)mag <= 1e-3) ? -1.0f : 1e10f;   // reference compares in double (F5)
-      if (pt > 0.f) {
-        lox = fminf(lox, px); loy = fminf(loy, py); loz = fminf(loz, pz);
-        hix = fmaxf(hix, px); hiy = fmaxf(hiy, py); hiz = fmaxf(hiz, pz);
-      }
-    }
-    sx[s * THREADS + tid] = px;
-    sy[s * THREADS + tid] = py;
-    sz[s * THREADS + tid] = pz;
-    if (XYZ_SMEM) sk16[s * THREADS + tid] = (uint16_t)kk[s];
-    x[s] = px; y[s] = py; z[s] = pz;
-    t[s] = pt;
-  }
-  // bounding box of the warp's selectable points
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-    loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-    loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
-  }
+  if (tid == 0) s_cnt = 0;
   const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float ox = p0x, oy = p0y, oz = p0z;
   int32_t *idx = p.idx + (size_t)scene * p.npoint;
   float *nxyz = p.new_xyz ? p.new_xyz + (size_t)scene * p.npoint * 3 : nullptr;
-  const bool writer = (rank == 0 && tid == THREADS - 1);
+  const bool writer = tid == FB_THREADS - 1;
   if (writer) {
     idx[0] = 0;
     if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
-    if (TRACK && p.strict_out) p.strict_out[scene] = 1;   // cleared by whoever sees a tie (ordered by the sync below)
+    if (p.strict_out) p.strict_out[scene] = 0;     // this kernel does not track ties: "unknown"
   }
-  const unsigned tx_bytes = 24u * C;
-  uint32_t r_slot0 = 0, r_slot1 = 0, r_bar0 = 0, r_bar1 = 0;
-  if (C > 1) {
-    if (tid == 0) {
-      fps_mbar_init(&c_bar[0], 1);
-      fps_mbar_init(&c_bar[1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      fps_mbar_arm(&c_bar[0], tx_bytes);
-      fps_mbar_arm(&c_bar[1], tx_bytes);
-    }
-    cluster.sync();
-    if (warp == 0 && lane < C) {
-      r_slot0 = mapa_cluster(fps_s2u(&c_cand[0][rank]), lane);
-      r_slot1 = mapa_cluster(fps_s2u(&c_cand[1][rank]), lane);
-      r_bar0 = mapa_cluster(fps_s2u(&c_bar[0]), lane);
-      r_bar1 = mapa_cluster(fps_s2u(&c_bar[1]), lane);
-    }
-  } else {
-    __syncthreads();
-  }
-  // The warp's candidate lives in w_cand (both buffers once it is stable); only its key is kept in a
-  // register for the cull test.  key 0 = nothing selectable.
-  unsigned ck = 0u;
-  bool fresh = false;                            // the first round must compute
-  bool stale = false;                            // the OTHER buffer still holds an older candidate
-  int my_k = -1;                                 // point index of the warp's candidate
-  int old = -2;                                  // the last pick
+  __syncthreads();
 
-  // arg-max over the lanes holding (key, v): largest key, then smallest v.  The common case (a unique
-  // maximum) costs two dependent redux; the ballot that detects ties issues alongside the second.
-  auto argmax_lane = [&](bool valid, unsigned key, unsigned v, unsigned &kmax, bool &tied) -> unsigned {
-    kmax = __reduce_max_sync(0xffffffffu, valid ? key : 0u);
-    const bool hit = valid && key == kmax;
-    unsigned src = __reduce_min_sync(0xffffffffu, hit ? lane : 32u);
+  // arg-max over the lanes holding (key, v): largest key, then smallest v (see fps_cull_kernel)
+  auto argmax_lane = [&](unsigned key, unsigned v, unsigned &kmax) -> unsigned {
+    kmax = __reduce_max_sync(0xffffffffu, key);
+    const bool hit = key == kmax;
     const unsigned ties = __ballot_sync(0xffffffffu, hit);
-    tied = kmax != 0u && (ties & (ties - 1u)) != 0u;
-    if (tied) src = fps_resolve_tie(hit, v, lane);   // rare
+    unsigned src = __ffs(ties) - 1u;
+    if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fps_resolve_tie(hit, v, lane);   // rare
     return src & 31u;
   };
-  // "Every pick so far was the strict unique maximum" (p.strict_out): then FPS over any prefix of the OUTPUT is
-  // the identity, which lets the next set-abstraction layers skip their sampling without the proof kernels.
-  // Kept off the round's dependency chain: ties between warps / CTAs are seen by every thread (`strict`), ties
-  // inside the winning warp or thread are checked lazily by the ONE thread that owns the round's winner, which
-  // then stores 0 (the flag was initialised to 1 before the first round).
-  bool strict = true;        // uniform: no tie at CTA / cluster level so far, and every round had a candidate
-  bool own_r = false;        // this lane published the warp's current candidate ...
-  bool wt_r = false;         // ... which tied with another lane of the warp
-  float best_r = -1.0f;      // this thread's best min-distance at its last update
-  int mk_r = -1;             // and the point that holds it
 
   for (int j = 1; j < p.npoint; ++j) {
-    const int buf = j & 1;
-    // ---- can this centre change any min-distance of the warp? -------------------------------------
-    // (the warp whose own candidate was just picked certainly must update: no test on the critical path)
-    bool skip = false;
-    if (fresh && old != my_k) {
-      const float ex = fmaxf(0.f, fmaxf(lox - ox, ox - hix)), ey = fmaxf(0.f, fmaxf(loy - oy, oy - hiy)),
-                  ez = fmaxf(0.f, fmaxf(loz - oz, oz - hiz));
-      const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;
-      skip = ck == 0u ? !(hix >= lox) : lb2 >= __uint_as_float(ck - 1u);
-    }
-    if (!skip) {
-      float bvv[P];
-      int bsi[P];
-#pragma unroll
-      for (int s = 0; s < P; ++s) {
-        const float d2 = XYZ_SMEM ? fminf(sqdist_ref(sx[s * THREADS + tid], sy[s * THREADS + tid],
-                                                     sz[s * THREADS + tid], ox, oy, oz), t[s])
-                                  : fminf(sqdist_ref(x[s], y[s], z[s], ox, oy, oz), t[s]);
-        t[s] = d2;
-        bvv[s] = d2;
-        bsi[s] = s;
+    // ---- 1. cull: which buckets can this centre change? -------------------------------------------
+    for (int b = tid; b < NB; b += FB_THREADS) {
+      const unsigned key = s_keyv[b].x;
+      if (key != 0u) {
+        const float4 b4 = s_box4[b];
+        const float2 b2 = s_box2[b];
+        const float ex = fmaxf(0.f, fmaxf(b4.x - ox, ox - b4.w)), ey = fmaxf(0.f, fmaxf(b4.y - oy, oy - b2.x)),
+                    ez = fmaxf(0.f, fmaxf(b4.z - oz, oz - b2.y));
+        const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;     // conservative w.r.t. fp32 rounding
+        if (lb2 < __uint_as_float(key - 1u)) s_list[atomicAdd(&s_cnt, 1)] = (uint16_t)b;
       }
-      // tournament over the slots (depth log2 P instead of a P-long dependent chain); the left operand
-      // always covers the lower slots, so strict '>' keeps the lowest slot (= lowest v) among equals
-#pragma unroll
-      for (int stride = 1; stride < P; stride *= 2) {
-#pragma unroll
-        for (int s = 0; s + stride < P; s += 2 * stride) {
-          if (bvv[s + stride] > bvv[s]) { bvv[s] = bvv[s + stride]; bsi[s] = bsi[s + stride]; }
-        }
-      }
-      const float best = bvv[0];
-      const int bs = bsi[0];
-      const float mx = sx[bs * THREADS + tid], my = sy[bs * THREADS + tid], mz = sz[bs * THREADS + tid];
-      const int mk = XYZ_SMEM ? (int)sk16[bs * THREADS + tid] : sk[bs * THREADS + tid];
-      const unsigned mv = XYZ_SMEM ? v_of_k((unsigned)mk) : sv[bs * THREADS + tid];
-      const unsigned key = best < 0.f ? 0u : __float_as_uint(best) + 1u;
-      bool wtied;
-      const unsigned wsrc = argmax_lane(true, key, mv, ck, wtied);
-      if (lane == wsrc) {
-        FpsCandV *e = &w_cand[buf][warp];
-        *reinterpret_cast<uint4 *>(e) = make_uint4(ck, mv, (unsigned)mk, __float_as_uint(mx));
-        *reinterpret_cast<float2 *>(&e->y) = make_float2(my, mz);
-      }
-      my_k = ck ? __shfl_sync(0xffffffffu, mk, wsrc) : -1;   // consumed next round only
-      if (TRACK) { own_r = lane == wsrc; wt_r = wtied; best_r = best; mk_r = mk; }
-      fresh = true;
-      stale = true;
-    } else if (stale) {
-      if (lane == 0) {
-        const FpsCandV *src = &w_cand[buf ^ 1][warp];
-        FpsCandV *dst = &w_cand[buf][warp];
-        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(src);
-        *reinterpret_cast<float2 *>(&dst->y) = *reinterpret_cast<const float2 *>(&src->y);
-      }
-      stale = false;
     }
     __syncthreads();
-    // ---- CTA arg-max, computed redundantly by every warp ------------------------------------------
-    uint4 e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-    float2 eyz = make_float2(0.f, 0.f);
-    if (lane < NW) {
-      e4 = *reinterpret_cast<const uint4 *>(&w_cand[buf][lane]);
-      eyz = *reinterpret_cast<const float2 *>(&w_cand[buf][lane].y);
-    }
-    unsigned bmax;
-    bool ctied;
-    unsigned src = argmax_lane(lane < NW, e4.x, e4.y, bmax, ctied);
-    unsigned bv = __shfl_sync(0xffffffffu, e4.y, src);
-    unsigned wk = __shfl_sync(0xffffffffu, e4.z, src);
-    if (TRACK) strict = strict && !ctied;
-    unsigned wxb = __shfl_sync(0xffffffffu, e4.w, src);
-    float wy = __shfl_sync(0xffffffffu, eyz.x, src);
-    float wz = __shfl_sync(0xffffffffu, eyz.y, src);
-    if (C > 1) {
-      if (warp == 0 && lane < C) {
-        const uint32_t rs = buf ? r_slot1 : r_slot0, rb = buf ? r_bar1 : r_bar0;
-        st_async_v4(rs, bmax, bv, wk, wxb, rb);
-        st_async_v2(rs + 16, __float_as_uint(wy), __float_as_uint(wz), rb);
-      }
-      fps_mbar_wait(&c_bar[buf], (unsigned)((j - 1) >> 1) & 1u);
-      if (tid == 0) fps_mbar_arm(&c_bar[buf], tx_bytes);
-      e4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-      eyz = make_float2(0.f, 0.f);
-      if (lane < C) {
-        e4 = *reinterpret_cast<const uint4 *>(&c_cand[buf][lane]);
-        eyz = *reinterpret_cast<const float2 *>(&c_cand[buf][lane].y);
-      }
-      src = argmax_lane(lane < C, e4.x, e4.y, bmax, ctied);
-      wk = __shfl_sync(0xffffffffu, e4.z, src);
-      if (TRACK) strict = strict && !ctied;
-      wxb = __shfl_sync(0xffffffffu, e4.w, src);
-      wy = __shfl_sync(0xffffffffu, eyz.x, src);
-      wz = __shfl_sync(0xffffffffu, eyz.y, src);
-    }
-    old = 0;
-    if (TRACK) strict = strict && bmax != 0u;
-    if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
-    else { ox = __uint_as_float(wxb); oy = wy; oz = wz; old = (int)wk; }
-    if (TRACK && own_r && bmax != 0u && old == mk_r) {   // one thread of the cluster per round
-      int eq = 0;
+    const int n = s_cnt;
+    // ---- 2. update the touched buckets: warp per bucket, U buckets in flight per warp -------------
+    for (int e0 = (int)warp; e0 < n; e0 += NW * U) {
+      float4 pt[U][PPL];
+      int kq[U][PPL];
+      int bb[U];
 #pragma unroll
-      for (int s = 0; s < P; ++s) eq += (t[s] == best_r) ? 1 : 0;
-      if (wt_r || eq > 1) p.strict_out[scene] = 0;
+      for (int u = 0; u < U; ++u) {
+        const int e = e0 + u * NW;
+        bb[u] = e < n ? (int)s_list[e] : -1;
+        if (bb[u] >= 0) {
+#pragma unroll
+          for (int q = 0; q < PPL; ++q) {
+            const int pos = bb[u] * BS + q * 32 + (int)lane;
+            pt[u][q] = pts[pos];
+            kq[u][q] = __ldg(kk + pos);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (bb[u] < 0) continue;                              // warp-uniform
+        unsigned bkey = 0u, bv = 0xffffffffu;
+        int bq = 0;
+#pragma unroll
+        for (int q = 0; q < PPL; ++q) {
+          const float4 v4 = pt[u][q];
+          const float t2 = fminf(sqdist_ref(v4.x, v4.y, v4.z, ox, oy, oz), v4.w);
+          if (t2 < v4.w) pts[bb[u] * BS + q * 32 + (int)lane].w = t2;
+          const unsigned key = t2 < 0.f ? 0u : __float_as_uint(t2) + 1u;
+          const unsigned v = fb_v_of_k((unsigned)kq[u][q], p.T, p.log2T, p.Q);
+          if (key > bkey || (key == bkey && key != 0u && v < bv)) { bkey = key; bv = v; bq = q; }
+        }
+        unsigned kmax;
+        const unsigned src = argmax_lane(bkey, bv, kmax);
+        if (lane == src) {
+          s_keyv[bb[u]] = make_uint2(kmax, bv);
+          float4 c = pt[u][0];
+          int ck = kq[u][0];
+#pragma unroll
+          for (int q = 1; q < PPL; ++q) if (bq == q) { c = pt[u][q]; ck = kq[u][q]; }
+          s_kxyz[bb[u]] = make_float4(__int_as_float(ck), c.x, c.y, c.z);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 3. select: arg-max over the bucket candidates ---------------------------------------------
+    if (tid == 0) s_cnt = 0;                                   // everybody has read n
+    unsigned mkey = 0u, mv = 0xffffffffu, mb = 0u;
+    for (int b = tid; b < NB; b += FB_THREADS) {
+      const uint2 kv = s_keyv[b];
+      if (kv.x > mkey || (kv.x == mkey && kv.x != 0u && kv.y < mv)) { mkey = kv.x; mv = kv.y; mb = (unsigned)b; }
+    }
+    unsigned wmax;
+    const unsigned wsrc = argmax_lane(mkey, mv, wmax);
+    if (lane == wsrc) s_wc[warp] = make_uint4(mkey, mv, mb, 0u);
+    __syncthreads();
+    uint4 c4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
+    if (lane < NW) c4 = s_wc[lane];
+    unsigned bmax;
+    const unsigned csrc = argmax_lane(c4.x, c4.y, bmax);
+    const unsigned wb = __shfl_sync(0xffffffffu, c4.z, csrc);
+    int old = 0;
+    if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
+    else {
+      const float4 w = s_kxyz[wb];
+      old = __float_as_int(w.x); ox = w.y; oy = w.z; oz = w.w;
     }
     if (writer) {
       idx[j] = old;
       if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
     }
   }
-  if (writer && p.strict_out && (!TRACK || !strict)) p.strict_out[scene] = 0;
-  if (C > 1) cluster.sync();
-}
-
-template <int P, int THREADS, bool XYZ_SMEM, bool TRACK>
-static int launch_fps_cull_t(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
-  auto kern = fps_cull_kernel<P, THREADS, XYZ_SMEM, TRACK>;
-  const size_t smem = XYZ_SMEM ? (size_t)P * THREADS * (3 * sizeof(float) + sizeof(uint16_t))
-                               : (size_t)5 * P * THREADS * sizeof(float);
-  static bool attr_set = false;   // per instantiation; the attribute is sticky for the process
-  if (!attr_set) {
-    SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(C, B, 1);
-  cfg.blockDim = dim3(THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = C;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SPC_CUDA(cudaLaunchKernelEx(&cfg, kern, p, perm));
-  return SPC_OK;
-}
-
-template <int P, int THREADS, bool XYZ_SMEM>
-static int launch_fps_cull(const FpsParams &p, const int32_t *perm, int B, int C, cudaStream_t stream) {
-  return p.strict_out ? launch_fps_cull_t<P, THREADS, XYZ_SMEM, true>(p, perm, B, C, stream)
-                      : launch_fps_cull_t<P, THREADS, XYZ_SMEM, false>(p, perm, B, C, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -891,71 +793,74 @@ using namespace spc;
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
                     int hint_ordered, const int32_t *known_ordered, int32_t *strict_out, void *workspace,
-                    size_t workspace_bytes, void *stream_);
+                    size_t workspace_bytes, int algo, void *stream_);
 
-// process-wide tuning knob (0 = automatic).  8-CTA clusters minimise the latency of one call;
-// 4-CTA clusters cost ~15 % more time per call but half the SM-time, which is what matters when
-// several batches are in flight on different streams (spacap3d_b200/pipeline.py).
-static int g_fps_cluster = 0;
-extern "C" int spc_set_fps_cluster(int cluster_ctas) {
-  if (cluster_ctas != 0 && cluster_ctas != 1 && cluster_ctas != 2 && cluster_ctas != 4 && cluster_ctas != 8 &&
-      cluster_ctas != 16) {
-    set_error("spc_set_fps_cluster: %d is not one of 0,1,2,4,8,16", cluster_ctas);
-    return SPC_ERR_INVALID_ARG;
-  }
-  g_fps_cluster = cluster_ctas;
-  return SPC_OK;
+// bucket size of the bucketed sampler for a cloud of N points (0 = not applicable): ~500-1300 buckets keep the
+// per-round scan of the bucket table at 2-5 entries per thread
+static int fb_bucket_size(int N) {
+  if (N < 4096 || N > FMS_THREADS * FMS_ITEMS) return 0;   // the Morton sort's capacity bounds this path
+  return N <= 20480 ? 32 : 64;
 }
+static size_t fb_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// process-wide switch for the Morton-sorted, culled kernel (0 = off, 1 = on).  Measured on B200, batch
-// 8 x 40 000 -> 2048: one call alone is ~15 % slower with it (0.67 vs 0.60 us per round: the explicit
-// tie-break and the cull test sit on the round's dependency chain, and the sort prepass is extra), but it
-// issues a fraction of the instructions, so a pipeline that keeps several batches in flight on different
-// streams gains ~5 % overall.  spacap3d_b200/pipeline.py turns it on; SPC_FPS_CULL=0/1 overrides.
-static int g_fps_cull = 0;
-extern "C" int spc_set_fps_cull(int on) {
-  if (on != 0 && on != 1 && on != 2 && on != 3) {
-    set_error("spc_set_fps_cull: %d is not 0, 1, 2 or 3", on);
-    return SPC_ERR_INVALID_ARG;
-  }
-  g_fps_cull = on;
-  return SPC_OK;
-}
-
+// workspace layout: D (B,npoint) f32 | ok (B) i32 | perm (B,N) i32 | [16-byte aligned] pts (B,NB*BS) float4 |
+// kk (B,NB*BS) i32 | boxes (B,NB,6) f32
 extern "C" size_t spc_fps_workspace_bytes(int B, int N, int npoint) {
-  // D (B,npoint) + ok (B) for the ordered-prefix proof, perm (B,N) for the Morton-sorted (culled) kernel
-  return ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B + (size_t)B * (size_t)(N > 0 ? N : 0)) * 4;
+  size_t bytes = ((size_t)B * (size_t)(npoint > 0 ? npoint : 0) + (size_t)B + (size_t)B * (size_t)(N > 0 ? N : 0)) * 4;
+  const int BS = fb_bucket_size(N);
+  if (BS) {
+    const size_t NB = ((size_t)N + BS - 1) / BS;
+    bytes = fb_align16(bytes) + (size_t)B * NB * BS * 20 + (size_t)B * NB * 24;
+  }
+  return bytes;
 }
 
 extern "C" int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint,
                                            int32_t *idx, float *new_xyz, void *stream_) {
-  return fps_impl(xyz, B, N, npoint, idx, new_xyz, 0, nullptr, nullptr, nullptr, 0, stream_);
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, 0, nullptr, nullptr, nullptr, 0, SPC_FPS_AUTO, stream_);
 }
 
 extern "C" int spc_furthest_point_sampling_ex(const float *xyz, int B, int N, int npoint,
                                               int32_t *idx, float *new_xyz, int hint_ordered,
                                               void *workspace, size_t workspace_bytes,
                                               void *stream_) {
-  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, nullptr, nullptr, workspace, workspace_bytes, stream_);
+  return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, nullptr, nullptr, workspace, workspace_bytes,
+                  SPC_FPS_AUTO, stream_);
 }
 
 extern "C" int spc_furthest_point_sampling_ex2(const float *xyz, int B, int N, int npoint, int32_t *idx,
                                                float *new_xyz, int hint_ordered, const int32_t *known_ordered,
                                                int32_t *strict_out, void *workspace, size_t workspace_bytes,
-                                               void *stream_) {
+                                               int algo, void *stream_) {
+  SPC_CHECK_ARG(algo == SPC_FPS_AUTO || algo == SPC_FPS_CLUSTER || algo == SPC_FPS_BUCKET,
+                "fps: algo %d is not one of SPC_FPS_AUTO / _CLUSTER / _BUCKET", algo);
   return fps_impl(xyz, B, N, npoint, idx, new_xyz, hint_ordered, known_ordered, strict_out, workspace,
-                  workspace_bytes, stream_);
+                  workspace_bytes, algo, stream_);
 }
 
-static int fps_cull_mode() {
-  if (const char *e = getenv("SPC_FPS_CULL")) return atoi(e);
-  return g_fps_cull;
+template <int BS, int U>
+static int launch_fps_bucket(const FpsParams &p, int B, int N, int32_t *perm, void *ws_tail, cudaStream_t stream) {
+  const int NB = (N + BS - 1) / BS;
+  float4 *pts = reinterpret_cast<float4 *>(ws_tail);
+  int32_t *kk = reinterpret_cast<int32_t *>(pts + (size_t)B * NB * BS);
+  float *boxes = reinterpret_cast<float *>(kk + (size_t)B * NB * BS);
+  const size_t sort_smem = (size_t)FMS_BINS * sizeof(int);
+  SPC_CUDA(cudaFuncSetAttribute(fps_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(p.xyz, N, perm);
+  SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
+  fps_bucket_build_kernel<BS><<<dim3(ceil_div(NB, 8), B), 256, 0, stream>>>(p.xyz, perm, N, NB, pts, kk, boxes);
+  SPC_LAUNCH_CHECK("fps_bucket_build_kernel");
+  auto kern = fps_bucket_kernel<BS, U>;
+  const size_t smem = (size_t)NB * 50;
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B, FB_THREADS, smem, stream>>>(p, pts, kk, boxes, NB);
+  SPC_LAUNCH_CHECK("fps_bucket_kernel");
+  return SPC_OK;
 }
-static bool fps_cull_enabled() { return fps_cull_mode() != 0; }
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
                     int hint_ordered, const int32_t *known_ordered, int32_t *strict_out, void *workspace,
-                    size_t workspace_bytes, void *stream_) {
+                    size_t workspace_bytes, int algo, void *stream_) {
   SPC_CHECK_ARG(B >= 0 && N >= 1 && npoint >= 0, "fps: bad sizes B=%d N=%d npoint=%d", B, N, npoint);
   SPC_CHECK_ARG(xyz && (idx || npoint == 0 || B == 0), "fps: null pointer");
   if (B == 0 || npoint == 0) return SPC_OK;
@@ -993,20 +898,50 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
       FPS_CASE(8, 256, true) FPS_CASE(16, 256, true)
     }
   }
+  // ---- bucketed sampler (points parked in L2, one small CTA per scene): needs the caller's workspace -------
+  const int BS = fb_bucket_size(N);
+  if (algo != SPC_FPS_CLUSTER && BS && workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) &&
+      npoint >= 2) {
+    const size_t head = ((size_t)B * npoint + (size_t)B + (size_t)B * N) * 4;
+    int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
+    void *tail = reinterpret_cast<char *>(workspace) + fb_align16(head);
+    SPC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps: workspace must be 16-byte aligned");
+    return BS == 32 ? launch_fps_bucket<32, 4>(p, B, N, perm, tail, stream)
+                    : launch_fps_bucket<64, 2>(p, B, N, perm, tail, stream);
+  }
+  if (algo == SPC_FPS_BUCKET) {
+    set_error("fps: SPC_FPS_BUCKET needs a workspace of spc_fps_workspace_bytes() and 4096 <= N <= %d (got N=%d)",
+              FMS_THREADS * FMS_ITEMS, N);
+    return SPC_ERR_UNSUPPORTED;
+  }
   // ---- clusters of 512-thread CTAs ------------------------------------------------------------
   // The rounds are latency-bound, so all B scenes should be co-resident.  Measured on B200
   // (B=8, N=40k): C=8 0.81 us/round, C=16 1.03 (slower exchange across a non-portable cluster),
-  // C=4 1.19 (xyz no longer fits in registers) -> prefer 8; SPC_FPS_CLUSTER overrides for tuning.
-  static int cached_max16 = -1, cached_max8 = -1;
-  if (cached_max8 < 0) cached_max8 = max_active_clusters<10, 512, true>(8);
+  // C=4 1.19 (xyz no longer fits in registers) -> prefer 8.
+  // The occupancy answers depend on the DEVICE (nn.DataParallel drives several from one process): cached per device.
+  static std::mutex occ_mutex;
+  static int cached_max16[64], cached_max8[64];
+  static bool cached_init = false;
+  int dev = 0;
+  SPC_CUDA(cudaGetDevice(&dev));
+  dev = dev < 0 || dev >= 64 ? 0 : dev;
+  int max8, max16 = -1;
+  {
+    std::lock_guard<std::mutex> lock(occ_mutex);
+    if (!cached_init) { for (int d = 0; d < 64; ++d) cached_max16[d] = cached_max8[d] = -1; cached_init = true; }
+    if (cached_max8[dev] < 0) cached_max8[dev] = max_active_clusters<10, 512, true>(8);
+    max8 = cached_max8[dev];
+  }
   int C = 8;
-  if (cached_max8 > 0 && cached_max8 < B) C = (B * 4 <= kNumSMs) ? 4 : 2;
-  if (g_fps_cluster) C = g_fps_cluster;
-  if (const char *e = getenv("SPC_FPS_CLUSTER")) { int c = atoi(e); if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) C = c; }
+  if (max8 > 0 && max8 < B) C = (B * 4 <= kNumSMs) ? 4 : 2;
   int need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512));
   while (need > 27 && C < 16) { C *= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
-  if (C == 16 && cached_max16 < 0) cached_max16 = max_active_clusters<6, 512, true>(16);
-  if (C == 16 && cached_max16 <= 0) {
+  if (C == 16) {
+    std::lock_guard<std::mutex> lock(occ_mutex);
+    if (cached_max16[dev] < 0) cached_max16[dev] = max_active_clusters<6, 512, true>(16);
+    max16 = cached_max16[dev];
+  }
+  if (C == 16 && max16 <= 0) {
     set_error("fps: N=%d needs a 16-CTA cluster which this device cannot schedule", N);
     return SPC_ERR_UNSUPPORTED;
   }
@@ -1015,54 +950,12 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
     return SPC_ERR_UNSUPPORTED;
   }
   while (C > 1 && need <= 1) { C /= 2; need = (int)((V + (long long)C * 512 - 1) / ((long long)C * 512)); }
-  // ---- Morton-sorted, culled kernel: needs the caller's workspace (perm) ----------------------------
-  if (workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) && N >= 8192 && npoint >= 64 &&
-      B <= 65535 && C <= 8 && fps_cull_enabled()) {
-    // mode 3: "full-SM" CTAs -- 768 threads x 20 points, ~215 KB of shared memory, clusters of ceil(N / 15360).
-    // The same work as mode 2 (three 256-thread CTAs per SM) but packed by construction: a 40 k-point scene holds
-    // exactly 3 SMs.  The hardware spreads the 64 small CTAs of a mode-2 batch over up to 64 SMs, where each of them
-    // blocks kernels that need a whole SM (the fused SA kernel) for the 1.5 ms the sampler runs.
-    const int cull_mode = fps_cull_mode();
-    const int TH = cull_mode == 3 ? 768 : 256;
-    const int Cc = cull_mode == 3 ? (int)(((long long)N + 768LL * 20 - 1) / (768LL * 20)) : C;
-    const int need256 = (int)(((long long)N + (long long)Cc * TH - 1) / ((long long)Cc * TH));
-    if (need256 <= 20 && Cc <= 8 && N <= FMS_THREADS * FMS_ITEMS) {
-      int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
-      const size_t sort_smem = (size_t)FMS_BINS * sizeof(int);
-      static bool sort_attr_set = false;
-      if (!sort_attr_set) {
-        SPC_CUDA(cudaFuncSetAttribute(fps_morton_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-        sort_attr_set = true;
-      }
-      fps_morton_sort_kernel<<<B, FMS_THREADS, sort_smem, stream>>>(xyz, N, perm);
-      SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
-      const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;
-      if (cull_mode == 3) {
-        switch (P256) {
-          case 8: return launch_fps_cull<8, 768, true>(p, perm, B, Cc, stream);
-          case 10: return launch_fps_cull<10, 768, true>(p, perm, B, Cc, stream);
-          case 16: return launch_fps_cull<16, 768, true>(p, perm, B, Cc, stream);
-          default: return launch_fps_cull<20, 768, true>(p, perm, B, Cc, stream);
-        }
-      }
-      const bool xyz_smem = cull_mode == 2;
-      switch (P256) {
-        case 8: return xyz_smem ? launch_fps_cull<8, 256, true>(p, perm, B, C, stream) : launch_fps_cull<8, 256, false>(p, perm, B, C, stream);
-        case 10: return xyz_smem ? launch_fps_cull<10, 256, true>(p, perm, B, C, stream) : launch_fps_cull<10, 256, false>(p, perm, B, C, stream);
-        case 16: return xyz_smem ? launch_fps_cull<16, 256, true>(p, perm, B, C, stream) : launch_fps_cull<16, 256, false>(p, perm, B, C, stream);
-        default: return xyz_smem ? launch_fps_cull<20, 256, true>(p, perm, B, C, stream) : launch_fps_cull<20, 256, false>(p, perm, B, C, stream);
-      }
-    }
-  }
   // 256-thread CTAs with 20 points per thread and TWO CTAs per SM whenever the cloud fits: fewer
   // warps per reduction level make a round faster (1.32 vs 1.51 ms for 40k -> 2048 at batch 8) and
-  // two latency-bound CTAs (of different scenes / batches) share one SM's issue slots, which halves
-  // the SM-time per scene (measured: 9.4k vs 7.2k scenes/s with 8 batches in flight).
-  // SPC_FPS_THREADS=512 restores the one-CTA-per-SM variant for A/B runs.
+  // two latency-bound CTAs (of different scenes / batches) share one SM's issue slots.
   {
-    const char *e = getenv("SPC_FPS_THREADS");
     const int need256 = (int)((V + (long long)C * 256 - 1) / ((long long)C * 256));
-    if (!(e && atoi(e) == 512) && need256 <= 20 && need256 > 4) {
+    if (need256 <= 20 && need256 > 4) {
       const int P256 = need256 <= 8 ? 8 : need256 <= 10 ? 10 : need256 <= 16 ? 16 : 20;
       switch (P256) {
         FPS_CASE(8, 256, true) FPS_CASE(10, 256, true) FPS_CASE(16, 256, true) FPS_CASE(20, 256, true)

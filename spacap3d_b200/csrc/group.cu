@@ -795,7 +795,7 @@ extern "C" int spc_group_points_grad_ex(const float *grad_out, const int32_t *id
   // once C is a few channels and the cloud is not huge relative to C (SA2-SA4, vote aggregation,
   // multiview SA1); otherwise the atomic kernel is faster.
   if (!workspace || need == 0 || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) || C < 4 ||
-      (long long)N > 512LL * C || B == 0 || B > 65535 || getenv("SPC_GROUP_GRAD_ATOMIC"))
+      (long long)N > 512LL * C || B == 0 || B > 65535)
     return spc_group_points_grad(grad_out, idx, B, C, N, npoint, nsample, grad_points, stream_);
   SPC_CHECK_ARG(grad_points && grad_out && idx, "group_points_grad: null pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -805,7 +805,7 @@ extern "C" int spc_group_points_grad_ex(const float *grad_out, const int32_t *id
   const size_t off_bytes = (size_t)B * g.H * (size_t)g.Np * sizeof(int);
   uint16_t *order = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(workspace) + off_bytes);
   const size_t build_smem = gg_build_smem(N, g.Sp, g.Np);
-  if (N <= GB_MAX_N && build_smem <= 220 * 1024 && !getenv("SPC_GROUP_GRAD_OLD_FILL")) {
+  if (N <= GB_MAX_N && build_smem <= 220 * 1024) {
     // histogram + scan + two-level stable sort in one kernel per (scene, partition)
     SPC_CUDA(cudaFuncSetAttribute(gg_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_smem));
     gg_build_kernel<<<dim3(g.H, B), GB_THREADS, build_smem, stream>>>(idx, N, S, g.Sp, g.H, g.Np, offsets, order);

@@ -16,9 +16,9 @@
 //            the pair, so it is hoisted out of the grouping: G[i] = W0f' . f_i is one plain GEMM per
 //            layer over the n points (npoint*nsample/n = 4..16x fewer MACs) and the kernel evaluates
 //            h1 = relu(G[idx] + W0x' . (p_i - c_j)/r + b0) -- the xyz term stays in fp32 inside the
-//            kernel (it is a difference of nearby points; G is bf16).
+//            kernel (it is a difference of nearby points; G is fp16).
 //   layer 1  D1[128 rows x C2]  = H1[128 x C1] . W1'^T             tcgen05.mma, M=128, N=C2
-//            h2 = relu(D1 + b1) -> bf16 -> shared memory (thread per row, TMEM lane = row)
+//            h2 = relu(D1 + b1) -> fp16 -> shared memory (thread per row, TMEM lane = row)
 //   layer 2  D2[C3 x 128 rows]  = W2'[C3 x C2] . H2^T              tcgen05.mma, TRANSPOSED so that a
 //            TMEM lane is an output CHANNEL and the 128 columns are the rows of the tile: the
 //            max over the nsample neighbours of a centre is then a register-only reduction.
@@ -36,9 +36,7 @@
 // a warp writing one whole row (row-wise gather) and 8 lanes writing the same chunk of 8
 // consecutive rows (epilogue, lane = row) are bank-conflict free, and no TMA descriptor is needed
 // for gathered data.
-#include <cuda_bf16.h>
-#include <stdlib.h>
-
+#include <cuda_fp16.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -104,7 +102,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T ; one thread issues for the CTA
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -139,15 +137,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a=b=BF16, both K-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format (bits 4-5) = 1 (F32), a_format (7-9) =
+// b_format (10-12) = 0 (F16; 1 would be BF16), both operands K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+// fp16 operands carry 11 significant bits (bf16: 8): the fused MLP lands ~8x closer to the fp32 reference for the
+// same tensor-pipe rate and shared-memory footprint.  Conversions saturate (cvt ... .satfinite) instead of
+// producing inf above 65504, a range the BN-folded activations of this network never approach.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout: [0,14) start address >> 4,
 // [16,30) leading byte offset >> 4, [32,46) stride byte offset >> 4, [46,48) version = 1,
 // [61,64) layout type) for the 128-byte-swizzle K-major layout (type 2): a row is 128 contiguous
-// bytes (64 bf16), 8-row groups are 1024 B apart (SBO), the 16-byte chunk c of row r sits at chunk
+// bytes (64 fp16), 8-row groups are 1024 B apart (SBO), the 16-byte chunk c of row r sits at chunk
 // position c ^ (r & 7) (Swizzle<3,4,3>); K beyond 64 elements continues in the next "K atom",
 // rows*128 bytes further.  The leading-byte-offset field is unused for swizzled K-major (= 1).
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
@@ -159,7 +161,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// byte offset of the 16-byte chunk (row, kc) of a [rows x K] bf16 operand in that layout
+// byte offset of the 16-byte chunk (row, kc) of a [rows x K] fp16 operand in that layout
 __device__ __forceinline__ uint32_t sw128_off(int row, int kc, int rows) {
   return (uint32_t)((kc >> 3) * rows * 128 + row * 128 + (((kc & 7) ^ (row & 7)) << 4));
 }
@@ -168,17 +170,17 @@ __device__ __forceinline__ uint32_t sw128_kstep(int kk, int rows) {
   return (uint32_t)((kk >> 2) * rows * 128 + (kk & 3) * 32);
 }
 
-// relu + round-to-nearest bf16 conversion + packing of two floats in ONE instruction
-// (cvt.rn.relu.bf16x2.f32: first source -> upper half, second source -> lower half)
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+// relu + round-to-nearest fp16 conversion (saturating) + packing of two floats in ONE instruction
+// (cvt.rn.satfinite.relu.f16x2.f32: first source -> upper half, second source -> lower half)
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t *>(&v);
+__device__ __forceinline__ __half to_f16_sat(float v) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+  return __ushort_as_half(r);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -186,20 +188,21 @@ struct SaFusedParams {
   const float *xyz;       // (B,n,3)
   const float *new_xyz;   // (B,np,3)
   const int32_t *idx;     // (B,np,ns)
-  const __nv_bfloat16 *G; // projected form: (B,n,C1) per-point feature projection (BN scale folded)
+  const __half *G; // projected form: (B,n,C1) per-point feature projection (BN scale folded)
   const float *feat;      // in-line form: (B,Cf,n) raw features or nullptr
   const float *W0;        // (C1, 3+Cf) folded, fp32; projected form: Cf = 0, i.e. the xyz columns only
   const float *b0;        // (C1)
   int Cf;
   float radius;           // divide relative xyz by this (1.0 when normalize_xyz is off)
-  const __nv_bfloat16 *W1;  // (C2,C1) folded, bf16 row-major
+  const __half *W1;  // (C2,C1) folded, fp16 row-major
   const float *b1;          // (C2)
-  const __nv_bfloat16 *W2;  // (C3,C2)
+  const __half *W2;  // (C3,C2)
   const float *b2;          // (C3)
   float *out;             // (B,C3,np)
-  __nv_bfloat16 *out_pm;  // optional (B,np,C3): the same result point-major in bf16 (next layer's GEMM input)
+  __half *out_pm;  // optional (B,np,C3): the same result point-major in fp16 (next layer's GEMM input)
   int B, n, np, ns;
   int num_tiles;          // B*np*ns/128
+  int min_tiles;          // host-side launch hint (see spc_sa_fused_forward_ex), unused on the device
   // in-line form, optional: the folded layer-0 weights BY VALUE, [c][k] with k = K0 holding the bias.  Kernel
   // parameters live in constant bank 0, so `fmaf(p.w0c[const], x, acc)` compiles to an FFMA with a c[0x0][..]
   // operand: no shared-memory load, no scoreboard wait (the LDS.128 weight loads and the FMAs waiting for them
@@ -235,7 +238,7 @@ __device__ __forceinline__ void sa_inline_issue(const SaFusedParams &p, int b, i
 
 template <int NIN>
 __device__ __forceinline__ void sa_inline_finish(const float (&raw)[NIN + 2], float inv_r, float (&in)[NIN]) {
-  // (p - c) / r as a multiplication by 1/r (this path feeds a bf16 MLP: a 1-ulp difference to the
+  // (p - c) / r as a multiplication by 1/r (this path feeds a fp16 MLP: a 1-ulp difference to the
   // reference's true division is far below the rounding of the next step)
   in[0] = (raw[0] - raw[3]) * inv_r;
   in[1] = (raw[1] - raw[4]) * inv_r;
@@ -263,10 +266,10 @@ __device__ __forceinline__ void sa_inline_compute(const float (&in)[NIN], int r,
       acc[6] = fmaf(wb.z, in[k], acc[6]); acc[7] = fmaf(wb.w, in[k], acc[7]);
     }
     uint4 o;
-    o.x = pack_relu_bf16x2(acc[0], acc[1]);
-    o.y = pack_relu_bf16x2(acc[2], acc[3]);
-    o.z = pack_relu_bf16x2(acc[4], acc[5]);
-    o.w = pack_relu_bf16x2(acc[6], acc[7]);
+    o.x = pack_relu_f16x2(acc[0], acc[1]);
+    o.y = pack_relu_f16x2(acc[2], acc[3]);
+    o.z = pack_relu_f16x2(acc[4], acc[5]);
+    o.w = pack_relu_f16x2(acc[6], acc[7]);
     *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = o;
   }
 }
@@ -286,15 +289,15 @@ __device__ __forceinline__ void sa_inline_compute_const(const SaFusedParams &p, 
       acc[c] = a;
     }
     uint4 o;
-    o.x = pack_relu_bf16x2(acc[0], acc[1]);
-    o.y = pack_relu_bf16x2(acc[2], acc[3]);
-    o.z = pack_relu_bf16x2(acc[4], acc[5]);
-    o.w = pack_relu_bf16x2(acc[6], acc[7]);
+    o.x = pack_relu_f16x2(acc[0], acc[1]);
+    o.y = pack_relu_f16x2(acc[2], acc[3]);
+    o.z = pack_relu_f16x2(acc[4], acc[5]);
+    o.w = pack_relu_f16x2(acc[6], acc[7]);
     *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = o;
   }
 }
 
-// Projected layer 0: ONE WARP PER ROW PAIR so that the gather of a 2*C1-byte G row (bf16) is a
+// Projected layer 0: ONE WARP PER ROW PAIR so that the gather of a 2*C1-byte G row (fp16) is a
 // coalesced request (2 L1 wavefronts per row instead of 16+ with lane = row), 16 rows in flight per
 // warp.  Lane = 8 consecutive channels of one row: one 16-byte load, 8 x (3 FMA + add + relu) with
 // this lane's xyz weights / bias in registers, one 16-byte store into the swizzled H1.
@@ -302,14 +305,14 @@ template <int C1, int NS>
 __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, int tile, int warp, int lane,
                                                         int my_idx, const float (&wx)[8][3], const float (&wb)[8],
                                                         uint8_t *sH1, int tiles_per_scene) {
-  constexpr int LPR = C1 / 8;                 // lanes per row (8 bf16 = 16 bytes each)
+  constexpr int LPR = C1 / 8;                 // lanes per row (8 fp16 = 16 bytes each)
   constexpr int RPI = 32 / LPR;               // rows per warp-wide load
   constexpr int NPASS = 16 / RPI;             // a warp owns 16 rows of the tile
   const int kc = lane % LPR;
   const int sub = lane / LPR;
   const int b = tile / tiles_per_scene;                                // tiles never straddle scenes
   const int j = ((tile - b * tiles_per_scene) * SA_ROWS + warp * 16) / NS;   // the 16 rows share one centre (ns >= 16)
-  const __nv_bfloat16 *Gb = p.G + (size_t)b * p.n * C1 + 8 * kc;
+  const __half *Gb = p.G + (size_t)b * p.n * C1 + 8 * kc;
   const float *Pb = p.xyz + (size_t)b * p.n * 3;
   const float *cc = p.new_xyz + ((size_t)b * p.np + j) * 3;
   const float cx = __ldg(cc), cy = __ldg(cc + 1), cz = __ldg(cc + 2);
@@ -325,7 +328,7 @@ __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, 
     for (int t = 0; t < HB; ++t) {
       const int i = __shfl_sync(0xffffffffu, my_idx, (t0 + t) * RPI + sub);   // lanes 0..15 hold idx of the 16 rows
       g[t] = __ldg(reinterpret_cast<const uint4 *>(Gb + (size_t)i * C1));
-      // (p - c) / r as a multiplication by 1/r: this path is the bf16 one (rtol 1e-2), a 1-ulp
+      // (p - c) / r as a multiplication by 1/r: this path is the fp16 one (rtol 1e-2), a 1-ulp
       // difference to the reference's true division is irrelevant here
       rx[t] = (__ldg(Pb + 3 * i + 0) - cx) * inv_r;
       ry[t] = (__ldg(Pb + 3 * i + 1) - cy) * inv_r;
@@ -338,10 +341,11 @@ __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, 
       uint32_t ow[4];
 #pragma unroll
       for (int c2 = 0; c2 < 4; ++c2) {
-        const float g0 = __uint_as_float(gw[c2] << 16), g1 = __uint_as_float(gw[c2] & 0xffff0000u);   // bf16 -> f32
+        const float2 g01 = __half22float2(*reinterpret_cast<const __half2 *>(&gw[c2]));                // fp16 -> f32
+        const float g0 = g01.x, g1 = g01.y;
         const float v0 = fmaf(wx[2 * c2][2], rz[t], fmaf(wx[2 * c2][1], ry[t], fmaf(wx[2 * c2][0], rx[t], g0 + wb[2 * c2])));
         const float v1 = fmaf(wx[2 * c2 + 1][2], rz[t], fmaf(wx[2 * c2 + 1][1], ry[t], fmaf(wx[2 * c2 + 1][0], rx[t], g1 + wb[2 * c2 + 1])));
-        ow[c2] = pack_relu_bf16x2(v0, v1);
+        ow[c2] = pack_relu_f16x2(v0, v1);
       }
       *reinterpret_cast<uint4 *>(sH1 + sw128_off(r, kc, SA_ROWS)) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
@@ -355,7 +359,7 @@ __device__ __forceinline__ void sa_produce_proj_rowwise(const SaFusedParams &p, 
 // CTA (tensor pipe 4-14 % active, ncu).  Here the five stages of consecutive tiles overlap:
 //   warps 0-7   PRODUCERS   gather + layer 0            -> H1[s]      (s = tile parity)
 //   warp  16    MMA ISSUER  one thread: MMA1(k) then MMA2(k-1)        (tcgen05, D in TMEM)
-//   warps 8-11  EPILOGUE 1  D1[s] -> relu(+b1) -> bf16  -> H2[s]
+//   warps 8-11  EPILOGUE 1  D1[s] -> relu(+b1) -> fp16  -> H2[s]
 //   warps 12-15 EPILOGUE 2  D2[u&1] -> max over nsample, +b2, relu -> out   (u = 128-channel unit)
 // Hand-offs are mbarriers: "full" barriers are arrived on by the producing threads (after a
 // generic->async proxy fence, because UMMA reads shared memory through the async proxy) or by
@@ -392,10 +396,10 @@ __device__ __forceinline__ void mbarrier_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(bar)) : "memory");
 }
 
-// Row-major bf16 weights (ROWS, 8*KCH) -> the swizzled UMMA layout in shared memory; 8 x 16-byte loads in flight
+// Row-major fp16 weights (ROWS, 8*KCH) -> the swizzled UMMA layout in shared memory; 8 x 16-byte loads in flight
 // per thread.
 template <int ROWS, int KCH, int NT>
-__device__ __forceinline__ void sa_stage_weights(uint8_t *dst, const __nv_bfloat16 *src, int t) {
+__device__ __forceinline__ void sa_stage_weights(uint8_t *dst, const __half *src, int t) {
   constexpr int N = ROWS * KCH;
   for (int base = 0; base < N; base += NT * 8) {
     uint4 v[8];
@@ -581,8 +585,8 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
   } else if (warp == 16) {
     // =============================== MMA ISSUER (one thread) =====================================
     if (lane == 0) {
-      constexpr uint32_t IDESC1 = make_idesc_bf16(128, C2);
-      constexpr uint32_t IDESC2 = make_idesc_bf16(128, SA_ROWS);
+      constexpr uint32_t IDESC1 = make_idesc_f16(128, C2);
+      constexpr uint32_t IDESC2 = make_idesc_f16(128, SA_ROWS);
       const uint32_t aH1 = s2u(sH1), aH2 = s2u(sH2), aW1 = s2u(sW1), aW2 = s2u(sW2);
       for (int k = 0; k <= nt; ++k) {
         if (k < nt) {                                            // D1[s] = H1[s] . W1'^T
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
           for (int kk = 0; kk < C1 / 16; ++kk) {
             const uint64_t da = make_smem_desc_sw128(aH1 + s * L::H1_BYTES + sw128_kstep(kk, SA_ROWS));
             const uint64_t db = make_smem_desc_sw128(aW1 + sw128_kstep(kk, C2));
-            umma_bf16(tmem_base + s * C2, da, db, IDESC1, kk > 0);
+            umma_f16(tmem_base + s * C2, da, db, IDESC1, kk > 0);
           }
           umma_commit(&d1_full[s]);
           umma_commit(&h1_empty[s]);
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
             for (int kk = 0; kk < C2 / 16; ++kk) {
               const uint64_t da = make_smem_desc_sw128(aW2 + h * 128 * 128 + sw128_kstep(kk, C3));
               const uint64_t db = make_smem_desc_sw128(aH2 + s * L::H2_BYTES + sw128_kstep(kk, SA_ROWS));
-              umma_bf16(tmem_base + L::TMEM_D2 + st * SA_ROWS, da, db, IDESC2, kk > 0);
+              umma_f16(tmem_base + L::TMEM_D2 + st * SA_ROWS, da, db, IDESC2, kk > 0);
             }
             umma_commit(&d2_full[st]);
           }
@@ -639,10 +643,10 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
           const float4 ba = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8);
           const float4 bb = *reinterpret_cast<const float4 *>(sB1 + col0 + c8 * 8 + 4);
           uint4 o;
-          o.x = pack_relu_bf16x2(v[c8 * 8 + 0] + ba.x, v[c8 * 8 + 1] + ba.y);
-          o.y = pack_relu_bf16x2(v[c8 * 8 + 2] + ba.z, v[c8 * 8 + 3] + ba.w);
-          o.z = pack_relu_bf16x2(v[c8 * 8 + 4] + bb.x, v[c8 * 8 + 5] + bb.y);
-          o.w = pack_relu_bf16x2(v[c8 * 8 + 6] + bb.z, v[c8 * 8 + 7] + bb.w);
+          o.x = pack_relu_f16x2(v[c8 * 8 + 0] + ba.x, v[c8 * 8 + 1] + ba.y);
+          o.y = pack_relu_f16x2(v[c8 * 8 + 2] + ba.z, v[c8 * 8 + 3] + ba.w);
+          o.z = pack_relu_f16x2(v[c8 * 8 + 4] + bb.x, v[c8 * 8 + 5] + bb.y);
+          o.w = pack_relu_f16x2(v[c8 * 8 + 6] + bb.z, v[c8 * 8 + 7] + bb.w);
           *reinterpret_cast<uint4 *>(h2 + sw128_off(r, (col0 >> 3) + c8, SA_ROWS)) = o;
         }
       }
@@ -666,8 +670,8 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
         const int ch = h * 128 + q * 32 + lane;
         const float bias = __ldg(p.b2 + ch);
         float *o = p.out + ((size_t)b * C3 + ch) * p.np + j0;
-        // optional point-major bf16 copy: lanes = consecutive channels => 64-byte coalesced stores
-        __nv_bfloat16 *opm = p.out_pm ? p.out_pm + ((size_t)b * p.np + j0) * C3 + ch : nullptr;
+        // optional point-major fp16 copy: lanes = consecutive channels => 64-byte coalesced stores
+        __half *opm = p.out_pm ? p.out_pm + ((size_t)b * p.np + j0) * C3 + ch : nullptr;
         float m64 = -INFINITY;
 #pragma unroll
         for (int cb = 0; cb < SA_ROWS; cb += 32) {
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
               for (int t = 1; t < NS; ++t) m = fmaxf(m, v[gI * NS + t]);
               const float res = fmaxf(m + bias, 0.f);
               o[cb / NS + gI] = res;
-              if (opm) opm[(size_t)(cb / NS + gI) * C3] = __float2bfloat16_rn(res);
+              if (opm) opm[(size_t)(cb / NS + gI) * C3] = to_f16_sat(res);
             }
           } else {                                               // NS == 64: two 32-column loads per centre
 #pragma unroll
@@ -689,7 +693,7 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
             if ((cb & 32) != 0) {
               const float res = fmaxf(m64 + bias, 0.f);
               o[cb / 64] = res;
-              if (opm) opm[(size_t)(cb / 64) * C3] = __float2bfloat16_rn(res);
+              if (opm) opm[(size_t)(cb / 64) * C3] = to_f16_sat(res);
               m64 = -INFINITY;
             }
           }
@@ -707,8 +711,6 @@ __global__ void __launch_bounds__(SAP_THREADS, OCC) sa_fused_pipe_kernel(const S
   }
 }
 
-static int g_sa_min_tiles = 0;
-
 template <int C1, int C2, int C3, int NS, bool MODE_PROJ, int OCC>
 static int launch_sa_pipe_occ(const SaFusedParams &p, cudaStream_t stream) {
   using L = SaPipeSmem<C1, C2, C3, OCC>;
@@ -720,8 +722,7 @@ static int launch_sa_pipe_occ(const SaFusedParams &p, cudaStream_t stream) {
   // Throughput knob: every CTA pays a fixed cost (weight staging, TMEM allocation, pipeline fill); with few
   // tiles per CTA that cost dominates and a smaller grid spends less SM-time for the same work (slower alone,
   // faster when other streams can use the freed SMs).
-  int min_tiles = g_sa_min_tiles;
-  if (const char *e = getenv("SPC_SA_MIN_TILES")) min_tiles = atoi(e);
+  const int min_tiles = p.min_tiles;
   if (min_tiles > 0) grid = max(1, min(grid, (p.num_tiles + min_tiles - 1) / min_tiles));
   kern<<<grid, SAP_THREADS, smem, stream>>>(p);
   SPC_LAUNCH_CHECK("sa_fused_pipe_kernel");
@@ -730,12 +731,11 @@ static int launch_sa_pipe_occ(const SaFusedParams &p, cudaStream_t stream) {
 
 // The narrow in-line configuration (SA1: 64,64,128) needs 94 KB of shared memory and 256 TMEM columns, so two CTAs
 // share an SM when the registers allow it (<= 56 per thread): 34 resident warps instead of 17 hide the latencies
-// that keep the single CTA at ~45 % issue utilisation.  SPC_SA_OCC=1 restores one CTA per SM for A/B runs.
+// that keep the single CTA at ~45 % issue utilisation.
 template <int C1, int C2, int C3, int NS, bool MODE_PROJ>
 static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
   if constexpr (!MODE_PROJ && 2 * C2 + 128 <= 256 && 2 * (SaPipeSmem<C1, C2, C3, 2>::TOTAL_INLINE + 1024) <= 227 * 1024) {
-    static const bool occ2 = []() { const char *e = getenv("SPC_SA_OCC"); return !(e && atoi(e) == 1); }();
-    if (occ2 && p.Cf <= 8) return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 2>(p, stream);
+    if (p.Cf <= 8) return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 2>(p, stream);
   }
   return launch_sa_pipe_occ<C1, C2, C3, NS, MODE_PROJ, 1>(p, stream);
 }
@@ -744,36 +744,30 @@ static int launch_sa_pipe(const SaFusedParams &p, cudaStream_t stream) {
 
 using namespace spc;
 
-extern "C" int spc_set_sa_min_tiles(int tiles_per_cta) {
-  if (tiles_per_cta < 0 || tiles_per_cta > 4096) {
-    set_error("spc_set_sa_min_tiles: %d out of range", tiles_per_cta);
-    return SPC_ERR_INVALID_ARG;
-  }
-  g_sa_min_tiles = tiles_per_cta;
-  return SPC_OK;
-}
-
 extern "C" int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *idx,
-                                    const void *G_bf16, const float *feat, const float *W0,
-                                    const float *b0, int Cf, float radius, const void *W1_bf16,
-                                    const float *b1, const void *W2_bf16, const float *b2, int B, int n,
+                                    const void *G_f16, const float *feat, const float *W0,
+                                    const float *b0, int Cf, float radius, const void *W1_f16,
+                                    const float *b1, const void *W2_f16, const float *b2, int B, int n,
                                     int npoint, int nsample, int C1, int C2, int C3, float *out,
-                                    void *out_pm_bf16, void *stream_) {
-  return spc_sa_fused_forward_ex(xyz, new_xyz, idx, G_bf16, feat, W0, b0, nullptr, nullptr, Cf, radius, W1_bf16, b1,
-                                 W2_bf16, b2, B, n, npoint, nsample, C1, C2, C3, out, out_pm_bf16, stream_);
+                                    void *out_pm_f16, void *stream_) {
+  return spc_sa_fused_forward_ex(xyz, new_xyz, idx, G_f16, feat, W0, b0, nullptr, nullptr, Cf, radius, W1_f16, b1,
+                                 W2_f16, b2, B, n, npoint, nsample, C1, C2, C3, out, out_pm_f16, 0, stream_);
 }
 
 extern "C" int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, const int32_t *idx,
-                                       const void *G_bf16, const float *feat, const float *W0,
+                                       const void *G_f16, const float *feat, const float *W0,
                                        const float *b0, const float *W0_host, const float *b0_host, int Cf,
-                                       float radius, const void *W1_bf16, const float *b1, const void *W2_bf16,
+                                       float radius, const void *W1_f16, const float *b1, const void *W2_f16,
                                        const float *b2, int B, int n, int npoint, int nsample, int C1, int C2,
-                                       int C3, float *out, void *out_pm_bf16, void *stream_) {
+                                       int C3, float *out, void *out_pm_f16, int min_tiles_per_cta,
+                                       void *stream_) {
   SPC_CHECK_ARG(B >= 0 && n >= 1 && npoint >= 0 && nsample >= 1, "sa_fused: bad sizes");
+  SPC_CHECK_ARG(min_tiles_per_cta >= 0 && min_tiles_per_cta <= 4096, "sa_fused: min_tiles_per_cta %d out of range",
+                min_tiles_per_cta);
   if (B == 0 || npoint == 0) return SPC_OK;
-  SPC_CHECK_ARG(xyz && new_xyz && idx && W0 && b0 && W1_bf16 && b1 && W2_bf16 && b2 && out,
+  SPC_CHECK_ARG(xyz && new_xyz && idx && W0 && b0 && W1_f16 && b1 && W2_f16 && b2 && out,
                 "sa_fused: null pointer");
-  const bool proj = G_bf16 != nullptr;
+  const bool proj = G_f16 != nullptr;
   SPC_CHECK_ARG(proj ? (Cf == 0) : (feat || Cf == 0), "sa_fused: missing layer-0 operands");
   const long long rows = (long long)B * npoint * nsample;
   if (rows % SA_ROWS != 0 || ((long long)npoint * nsample) % SA_ROWS != 0) {
@@ -785,11 +779,12 @@ extern "C" int spc_sa_fused_forward_ex(const float *xyz, const float *new_xyz, c
     return SPC_ERR_UNSUPPORTED;
   }
   SaFusedParams p;
-  p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.G = (const __nv_bfloat16 *)G_bf16; p.feat = feat;
+  p.xyz = xyz; p.new_xyz = new_xyz; p.idx = idx; p.G = (const __half *)G_f16; p.feat = feat;
   p.W0 = W0; p.b0 = b0; p.Cf = Cf; p.radius = radius;
-  p.W1 = (const __nv_bfloat16 *)W1_bf16; p.b1 = b1; p.W2 = (const __nv_bfloat16 *)W2_bf16; p.b2 = b2;
-  p.out = out; p.out_pm = (__nv_bfloat16 *)out_pm_bf16; p.B = B; p.n = n; p.np = npoint; p.ns = nsample;
+  p.W1 = (const __half *)W1_f16; p.b1 = b1; p.W2 = (const __half *)W2_f16; p.b2 = b2;
+  p.out = out; p.out_pm = (__half *)out_pm_f16; p.B = B; p.n = n; p.np = npoint; p.ns = nsample;
   p.num_tiles = (int)(rows / SA_ROWS);
+  p.min_tiles = min_tiles_per_cta;
   p.use_w0c = 0;
   if (!proj && W0_host && b0_host && C1 * (4 + Cf) <= SA_W0C_MAX) {
     const int K0 = 3 + Cf, NIN = K0 + 1;

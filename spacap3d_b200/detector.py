@@ -19,21 +19,33 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _ext
-from .pointnet2_modules import FoldedChain, PointnetFPModule, PointnetSAModuleVotes, fast_eval_ok
+from .pointnet2_modules import (FoldedChain, PointnetFPModule, PointnetSAModuleVotes, _cache_of, attach_pm, fast_eval_ok,
+                                get_pm)
 
-# ScanNet per-class mean box sizes (18 x 3, float64): dataset metadata shipped by the reference as
+# ScanNet per-class mean box sizes (18 x 3, float64, every digit: the decoded corners must equal the reference's
+# bit for bit): dataset metadata shipped by the reference as
 # data/scannet/meta_data/scannet_reference_means.npz, read by ScannetDatasetConfig
 # (data/scannet/model_util_scannet.py:90).
 SCANNET_MEAN_SIZE_ARR = np.array([
-    [0.7750491, 0.94897728, 0.96542059], [1.86903267, 1.83214712, 1.19222992],
-    [0.61214778, 0.61928731, 0.70480848], [1.44113898, 1.60452036, 0.83652295],
-    [1.04780726, 1.20164188, 0.63457007], [0.56101232, 0.60847217, 1.71950401],
-    [1.07894895, 0.82033996, 1.16921199], [0.84171092, 1.35047945, 1.6898925],
-    [0.23051737, 0.47640499, 0.56569256], [1.45484899, 1.97119895, 0.2864328],
-    [1.07858031, 1.53705113, 0.86501906], [1.43119644, 0.76923111, 1.64982673],
-    [0.62969194, 0.70871287, 1.31433587], [0.43925034, 0.41569594, 1.70002748],
-    [0.58504462, 0.57878438, 0.72029611], [0.51158693, 0.50960673, 0.3128736],
-    [1.17320759, 1.0598714, 0.51812528], [0.43294385, 0.51933507, 0.48437456]], dtype=np.float64)
+    [0.7750491029714929, 0.9489772784305719, 0.9654205889420883],
+    [1.8690326739217817, 1.8321471223511647, 1.1922299150646347],
+    [0.6121477783923587, 0.6192873075057846, 0.7048084833710475],
+    [1.4411389838393118, 1.6045203579823017, 0.8365229505964112],
+    [1.0478072557954565, 1.2016418836390361, 0.6345700676484581],
+    [0.5610123179013166, 0.6084721692226233, 1.7195040055943263],
+    [1.0789489470730143, 0.8203399609681988, 1.1692119917347412],
+    [0.8417109198057999, 1.3504794475570598, 1.689892503247653],
+    [0.2305173710207977, 0.4764049876932717, 0.5656925618884787],
+    [1.4548489887322953, 1.9711989456815506, 0.28643280467880305],
+    [1.0785803060791836, 1.5370511310202535, 0.8650190604735265],
+    [1.4311964378217468, 0.7692311116413818, 1.6498267253793382],
+    [0.6296919388045009, 0.7087128690976665, 1.314335867333314],
+    [0.4392503422374527, 0.41569593879911637, 1.7000274790657892],
+    [0.5850446242623347, 0.5787843832293073, 0.7202961145680844],
+    [0.5115869258698381, 0.5096067340403306, 0.3128736034402105],
+    [1.1732075942887201, 1.0598714035004377, 0.5181252788752317],
+    [0.43294385021345605, 0.5193350711870748, 0.4843745602902239],
+], dtype=np.float64)
 
 NUM_CLASS = 18
 NUM_HEADING_BIN = 1
@@ -115,22 +127,20 @@ class VotingModule(nn.Module):
 
     def forward_normalized_fast(self, seed_xyz, seed_features):
         """Eval fast path returning (vote_xyz, L2-normalised vote_features) or None: three point-major
-        bf16 GEMMs (BN folded, bias+ReLU in the GEMM epilogue, the last one with fp32 output) and ONE
+        fp16 GEMMs (BN folded, bias+ReLU in the GEMM epilogue, the last one with fp32 output) and ONE
         tail kernel for offsets, residual, normalisation and both output layouts."""
-        pm = getattr(seed_features, "_spc_pm", None)
+        pm = get_pm(seed_features)
         if (self.training or self.vote_factor != 1 or pm is None or self.out_dim > 256
                 or not fast_eval_ok(seed_xyz, seed_features)):
             return None
-        chain = self.__dict__.setdefault("_chain", FoldedChain()).get(
-            [(self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, None)])
+        chain = _cache_of(self, FoldedChain).get([(self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, None)])
         B, S, D = pm.shape
         h = pm.reshape(B * S, D)
         h = torch._addmm_activation(chain[0][1], h, chain[0][0])
         h = torch._addmm_activation(chain[1][1], h, chain[1][0])
         net = torch.mm(h, chain[2][0], out_dtype=torch.float32)          # (B*S, 3+D), bias added in the tail
         vote_xyz, vote_features, vote_pm = _ext.vote_tail(net, chain[2][2], seed_xyz.contiguous(), pm)
-        vote_features._spc_pm = vote_pm
-        return vote_xyz, vote_features
+        return vote_xyz, attach_pm(vote_features, vote_pm)
 
 
 class ProposalModule(nn.Module):
@@ -166,9 +176,9 @@ class ProposalModule(nn.Module):
         data_dict["aggregated_vote_xyz"] = xyz
         data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
         data_dict["aggregated_vote_inds"] = fps_inds
-        pm = getattr(features, "_spc_pm", None)
+        pm = get_pm(features)
         if not self.training and pm is not None and fast_eval_ok(features):
-            chain = self.__dict__.setdefault("_chain", FoldedChain()).get(
+            chain = _cache_of(self, FoldedChain).get(
                 [(self.proposal[0], self.proposal[1]), (self.proposal[3], self.proposal[4]), (self.proposal[6], None)])
             B, K, D = pm.shape
             h = torch._addmm_activation(chain[0][1], pm.reshape(B * K, D), chain[0][0])

@@ -19,21 +19,13 @@ class GraphedDetector:
     replays the graph and (optionally) copies the requested outputs to pinned host buffers; it
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
-    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, fps_cluster=None,
-                 fps_cull=2, sa_min_tiles=16):
+    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, sa_min_tiles=16):
         assert example.is_cuda
-        # FPS cluster size: automatic (8 CTAs of 256 threads, two CTAs per SM) unless overridden
-        if fps_cluster is None:
-            fps_cluster = 0
-        from . import _lib
-        _lib.call("spc_set_fps_cluster", int(fps_cluster))
-        # several batches in flight: what limits throughput is how many SMs the latency-bound FPS calls
-        # occupy, not how long one call takes.  Mode 2 (culled, coordinates in shared memory, three CTAs
-        # per SM) takes 1.63 ms per call instead of 1.24 but a scene holds 2.7 SMs instead of 4:
-        # +10 % scenes/s over mode 1 and +14 % over the plain kernel at 12 streams (B200, 8 x 40k).
-        _lib.call("spc_set_fps_cull", int(fps_cull))
-        # same reasoning for the fused SA kernel: fewer, longer-lived CTAs for the small layers
-        _lib.call("spc_set_sa_min_tiles", int(sa_min_tiles))
+        # Launch hints baked into the captured graphs (per call and thread-local: nothing process-wide changes).
+        # With several batches in flight the fused SA kernel does better with fewer, longer-lived CTAs for the
+        # small layers (every CTA pays a fixed weight-staging cost).
+        from . import _ext
+        self._options = dict(sa_min_tiles=int(sa_min_tiles))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)
@@ -43,15 +35,17 @@ class GraphedDetector:
         self.graphs, self.outputs, self.host_out, self.done = [], [], [], []
         self.packed, self.host_packed = [], []
         self._next = 0
+        self._pending_host = [False] * self.n
+        self._submitted = [False] * self.n
         for s, x in zip(self.streams, self.static_in):
             x.copy_(example)
             s.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(s), torch.no_grad():
+            with torch.cuda.stream(s), torch.no_grad(), _ext.launch_options(**self._options):
                 for _ in range(warmup):                      # lazy inits (weight folding, func attrs)
                     model({"point_clouds": x})
             s.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s), torch.no_grad():
+            with torch.cuda.graph(g, stream=s), torch.no_grad(), _ext.launch_options(**self._options):
                 out = model({"point_clouds": x})
                 # the requested results are packed into ONE byte buffer inside the graph, so that a step
                 # needs a single device->host copy instead of one per tensor (8 small copies per step
@@ -89,20 +83,40 @@ class GraphedDetector:
         return {k: host[off:off + nbytes].view(out[k].dtype).view(out[k].shape) for k, off, nbytes in segs}
 
     def submit(self, x, to_host=False):
+        """Queue one batch on the next slot.  A device-resident `x` may still be being written on the caller's
+        current stream (e.g. by DeviceSceneStore.make_batch): the slot stream waits for that stream first.
+        With to_host=True the slot's pinned result buffer is overwritten, so the previous submission of the slot
+        must have been consumed with wait() (checked)."""
         i = self._next
+        if to_host and self._pending_host[i]:
+            raise RuntimeError("GraphedDetector.submit: slot %d still holds unread host results; call wait(%d) first" % (i, i))
         self._next = (i + 1) % self.n
         s = self.streams[i]
+        if x.is_cuda:
+            s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             self.static_in[i].copy_(x, non_blocking=True)
             self.graphs[i].replay()
             if to_host and self.result_keys:
                 self.host_packed[i].copy_(self.packed[i], non_blocking=True)
+                self._pending_host[i] = True
             self.done[i].record(s)
+        self._submitted[i] = True
         return i
+
+    def busy(self, i):
+        """True when slot i has a submission whose host results have not been collected with wait()."""
+        return self._pending_host[i]
 
     def wait(self, i):
         self.done[i].synchronize()
+        self._pending_host[i] = False
         return self.host_out[i] if self.host_out else self.outputs[i]
+
+    def close(self):
+        """Drain every stream."""
+        self.wait_all()
+        self._pending_host = [False] * self.n
 
     def wait_all(self):
         for s in self.streams:

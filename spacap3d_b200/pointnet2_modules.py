@@ -24,13 +24,6 @@ from . import _lib
 FAST_PATHS = True
 
 
-import os as _os
-# Chain the samplers through spc_furthest_point_sampling_ex2's "strict sequence" flags (SA2-SA4 then skip the
-# proof kernels as well).  Exact and tested, but measured neutral on B200 (the tie tracking slows the culled SA1
-# kernel by 2 %, which cancels the ~3 % saved on the proof kernels: 11.7-11.9 k scenes/s either way), so off.
-FPS_STRICT_FLAGS = _os.environ.get("SPC_FPS_STRICT", "0") == "1"
-
-
 def _sample_centres(xyz, npoint, inds=None):
     """FPS (unless indices are supplied) + gather of the sampled coordinates.
     Returns (new_xyz (B,npoint,3) or None, inds)."""
@@ -41,18 +34,9 @@ def _sample_centres(xyz, npoint, inds=None):
         # one kernel: the FPS epilogue already holds the winners' coordinates.  Centres produced by
         # an FPS are tagged so that the next layer can try the verified "already FPS-ordered"
         # shortcut (exact: see spc_furthest_point_sampling_ex).
-        # `_spc_fps_strict` carries the producing call's per-scene "strict sequence" flags: flagged scenes
-        # need neither the proof nor the rounds.
         hint = bool(getattr(xyz, "_spc_fps_ordered", False))
-        if not FPS_STRICT_FLAGS:
-            inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
-            new_xyz._spc_fps_ordered = True
-            return new_xyz, inds
-        known = getattr(xyz, "_spc_fps_strict", None) if hint and npoint <= xyz.shape[1] else None
-        inds, new_xyz, strict = _ext.furthest_point_sampling_with_xyz(
-            xyz.contiguous(), npoint, hint_ordered=hint, known_ordered=known, want_strict=True)
+        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
         new_xyz._spc_fps_ordered = True
-        new_xyz._spc_fps_strict = strict
         return new_xyz, inds
     if inds is None:
         inds = pointnet2_utils.furthest_point_sample(xyz, npoint)
@@ -62,6 +46,55 @@ def _sample_centres(xyz, npoint, inds=None):
 
 
 INLINE_MAX_FEATURES = 16   # raw feature channels the fused kernel evaluates in-line (layer 0)
+
+
+def attach_pm(t, pm):
+    """Tag fp32 tensor `t` (B,C,n) with its point-major 16-bit copy `pm` (B,n,C) for the next fast-path stage.
+    The tag records t's version counter and storage pointer: any in-place edit of `t` between layers
+    (`features.mul_(mask)`, in-place dropout, `copy_`) invalidates the copy instead of being silently ignored."""
+    t._spc_pm = (pm, t._version, t.data_ptr())
+    return t
+
+
+def get_pm(t):
+    """The point-major copy attached to `t` by attach_pm, or None when absent, stale or mis-shaped."""
+    tag = getattr(t, "_spc_pm", None)
+    if tag is None:
+        return None
+    pm, version, ptr = tag
+    if version != t._version or ptr != t.data_ptr() or pm.device != t.device or t.dim() != 3 \
+            or pm.shape != (t.shape[0], t.shape[2], t.shape[1]):
+        return None
+    return pm
+
+
+# BN-folded weight caches live OUTSIDE the modules' __dict__: nn.DataParallel's replicate() shallow-copies that
+# dict, which would make every replica (one per device and thread) share and overwrite one cache object.
+# Keyed weakly by module, so a replica's cache dies with the replica.
+import threading as _threading
+import weakref as _weakref
+_CACHES = _weakref.WeakKeyDictionary()
+_CACHES_LOCK = _threading.Lock()
+
+
+def _cache_of(module, factory):
+    with _CACHES_LOCK:
+        c = _CACHES.get(module)
+        if c is None:
+            c = _CACHES[module] = factory()
+        return c
+
+
+def invalidate_folded_caches(model=None):
+    """Drop the cached BN-folded weights of `model`'s modules (all modules when None).  The caches refresh
+    themselves when a parameter / running statistic changes through autograd-visible in-place ops (tensor version
+    counters); writes through `param.data` or raw pointers do not bump a version and need this call."""
+    with _CACHES_LOCK:
+        if model is None:
+            _CACHES.clear()
+        else:
+            for m in model.modules():
+                _CACHES.pop(m, None)
 
 
 def _fold_conv_bn(block):
@@ -107,11 +140,11 @@ class _FoldedMLP:
         return self._host0
 
     def w0f(self, W0):
-        """(C1, Cf) bf16: feature columns of the folded conv0 for the projection GEMM (F.linear: the "TN" layout,
+        """(C1, Cf) fp16: feature columns of the folded conv0 for the projection GEMM (F.linear: the "TN" layout,
         for which cuBLAS picks its sm_100 kernels; the transposed "NN" form got a legacy sm_75 tensor-op kernel
         for the 16384 x 128 x 128 case, 24 us instead of ~7)."""
         if self._w0f_t is None:
-            self._w0f_t = W0[:, 3:].contiguous().to(torch.bfloat16)
+            self._w0f_t = W0[:, 3:].contiguous().to(_ext.HALF)
         return self._w0f_t
 
     def w0x(self, W0):
@@ -122,7 +155,7 @@ class _FoldedMLP:
 
     def get(self, mlp):
         tensors = [t for t in list(mlp.parameters()) + list(mlp.buffers())]
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
         if key != self.key:
             self.key = key
             self.data = None
@@ -133,8 +166,8 @@ class _FoldedMLP:
                 if all(f is not None for f in folded):
                     (W0, b0), (W1, b1), (W2, b2) = folded
                     self.data = (W0.contiguous(), b0.contiguous(),
-                                 W1.to(torch.bfloat16).contiguous(), b1.contiguous(),
-                                 W2.to(torch.bfloat16).contiguous(), b2.contiguous())
+                                 W1.to(_ext.HALF).contiguous(), b1.contiguous(),
+                                 W2.to(_ext.HALF).contiguous(), b2.contiguous())
         return self.data
 
 
@@ -150,7 +183,7 @@ def fold_conv_bn_pair(conv, bn):
 
 
 class FoldedChain:
-    """Cache of a conv(+BN)(+ReLU) chain as point-major GEMM operands: [(W^T (Cin,Cout) bf16, b bf16)],
+    """Cache of a conv(+BN)(+ReLU) chain as point-major GEMM operands: [(W^T (Cin,Cout) fp16, b fp16)],
     refreshed when a parameter / running statistic changes (tensor versions)."""
 
     def __init__(self):
@@ -162,19 +195,19 @@ class FoldedChain:
         tensors = []
         for conv, bn in pairs:
             tensors += list(conv.parameters()) + (list(bn.parameters()) + list(bn.buffers()) if bn is not None else [])
-        key = tuple((t.data_ptr(), t._version) for t in tensors)
+        key = tuple((t.data_ptr(), t._version, t.device) for t in tensors)
         if key != self.key:
             self.key = key
             self.layers = []
             for conv, bn in pairs:
                 W, b = fold_conv_bn_pair(conv, bn)
-                self.layers.append((W.t().contiguous().to(torch.bfloat16), b.to(torch.bfloat16).contiguous(),
+                self.layers.append((W.t().contiguous().to(_ext.HALF), b.to(_ext.HALF).contiguous(),
                                     b.contiguous()))
         return self.layers
 
 
 def fast_eval_ok(*tensors):
-    """The bf16 point-major fast paths apply in eval-style use only: no autograd, CUDA tensors."""
+    """The fp16 point-major fast paths apply in eval-style use only: no autograd, CUDA tensors."""
     return FAST_PATHS and not torch.is_grad_enabled() and all(t is not None and t.is_cuda for t in tensors)
 
 
@@ -299,7 +332,7 @@ class PointnetSAModuleVotes(nn.Module):
                 or not isinstance(self.grouper, pointnet2_utils.QueryAndGroup)
                 or self.grouper.sample_uniformly or (features is not None and features.dtype != torch.float32)):
             return None
-        cache = self.__dict__.setdefault("_folded", _FoldedMLP())
+        cache = _cache_of(self, _FoldedMLP)
         folded = cache.get(self.mlp_module)
         if folded is None:
             return None
@@ -317,17 +350,16 @@ class PointnetSAModuleVotes(nn.Module):
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, feat=feat,
                                                     radius=radius, want_point_major=True, W0_host=W0h, b0_host=b0h)
             else:
-                # conv0 hoisted out of the grouping: ONE bf16 GEMM over the n points gives the
+                # conv0 hoisted out of the grouping: ONE fp16 GEMM over the n points gives the
                 # per-point feature projection; the xyz columns stay in fp32 inside the kernel
-                pm = getattr(features, "_spc_pm", None)        # point-major bf16 copy from the producer
-                if pm is None or pm.shape != (features.shape[0], features.shape[2], Cf):
-                    pm = features.transpose(1, 2).to(torch.bfloat16)
+                pm = get_pm(features)                          # point-major fp16 copy from the producer
+                if pm is None:
+                    pm = features.transpose(1, 2).to(_ext.HALF)
                 Bn = pm.shape[0] * pm.shape[1]
                 G = torch.nn.functional.linear(pm.reshape(Bn, Cf), cache.w0f(W0)).view(pm.shape[0], pm.shape[1], -1)
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, cache.w0x(W0), b0, W1, b1, W2, b2,
                                                     G=G, radius=radius, want_point_major=True)
-            out._spc_pm = out_pm       # lets the next layer skip its transpose + cast
-            return out
+            return attach_pm(out, out_pm)       # lets the next layer skip its transpose + cast
         except _lib.SpcUnsupported:
             return None
 
@@ -378,14 +410,14 @@ class PointnetFPModule(nn.Module):
         return self.mlp(new_features.unsqueeze(-1)).squeeze(-1)
 
 
-    # -- bf16 point-major eval path -------------------------------------------------------------------
+    # -- fp16 point-major eval path -------------------------------------------------------------------
     def _forward_fast(self, unknown, known, unknow_feats, known_feats):
-        """three_nn+weights (1 kernel) -> interpolate+concat (1 kernel, point-major bf16) -> one
+        """three_nn+weights (1 kernel) -> interpolate+concat (1 kernel, point-major fp16) -> one
         cuBLASLt GEMM with fused bias+ReLU per MLP layer -> channel-major fp32 copy for the API.
-        Needs the point-major bf16 copies that the fused SA / FP kernels attach to their outputs."""
+        Needs the point-major fp16 copies that the fused SA / FP kernels attach to their outputs."""
         if self.training or known is None or not fast_eval_ok(unknown, known, unknow_feats, known_feats):
             return None
-        kpm, spm = getattr(known_feats, "_spc_pm", None), getattr(unknow_feats, "_spc_pm", None)
+        kpm, spm = get_pm(known_feats), get_pm(unknow_feats)
         if kpm is None or spm is None or known.shape[1] < 3 or kpm.shape[2] % 8 or spm.shape[2] % 8:
             return None
         pairs = []
@@ -394,7 +426,7 @@ class PointnetFPModule(nn.Module):
             if conv is None or not isinstance(act, nn.ReLU) or conv.kernel_size != (1, 1):
                 return None
             pairs.append((conv, norm.bn if norm is not None else None))
-        chain = self.__dict__.setdefault("_chain", FoldedChain()).get(pairs)
+        chain = _cache_of(self, FoldedChain).get(pairs)
         if chain[0][0].shape[0] != kpm.shape[2] + spm.shape[2]:
             return None
         idx, weight = _ext.three_nn_weights(unknown.contiguous(), known.contiguous())
@@ -404,9 +436,7 @@ class PointnetFPModule(nn.Module):
         for Wt, b16, _ in chain:
             h = torch._addmm_activation(b16, h, Wt)          # relu(h @ Wt + b), bias+ReLU in the GEMM epilogue
         out_pm = h.view(B, n, -1)
-        out = _ext.pm_to_cm(out_pm)
-        out._spc_pm = out_pm
-        return out
+        return attach_pm(_ext.pm_to_cm(out_pm), out_pm)
 
 
 class PointnetLFPModuleMSG(nn.Module):

@@ -42,51 +42,41 @@ def test_fps(ext, ref_ext, name):
     np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
 
 
+ALGOS = ("auto", "cluster", "bucket")
+
+
+def _algo(ext, name):
+    return ext.launch_options(fps_algo={"auto": ext.FPS_AUTO, "cluster": ext.FPS_CLUSTER, "bucket": ext.FPS_BUCKET}[name])
+
+
 @pytest.mark.parametrize("name", list(cases.fps_large_cases().keys()))
-def test_fps_large_clouds(ext, name, monkeypatch):
-    """N >= 8192: the Morton-sorted, culled kernel (workspace given), the plain cluster kernel (no
-    workspace, or culling off) and the oracle all agree bit for bit."""
+def test_fps_large_clouds(ext, name):
+    """N >= 8192: the bucketed sampler (Morton-sorted points parked in L2, one CTA per scene), the cluster
+    sampler (everything on-chip) and the oracle all agree bit for bit -- lattices with exact ties everywhere,
+    heavy duplicates, planes / lines, all-identical points included."""
     xyz, m = cases.fps_large_cases()[name]
     want = oracle.furthest_point_sampling(xyz, m)
-    for mode in ("1", "2", "3"):  # coordinates in registers / in shared memory (three CTAs per SM) / full-SM CTAs
-        monkeypatch.setenv("SPC_FPS_CULL", mode)
-        got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
-        np.testing.assert_array_equal(got, want)
-        idx2, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m, hint_ordered=True)
-        np.testing.assert_array_equal(idx2.cpu().numpy(), want)
+    for algo in ALGOS:
+        if algo == "bucket" and not 4096 <= xyz.shape[1] <= 40960:
+            continue                                   # outside the bucketed sampler's range (refused, see below)
+        with _algo(ext, algo):
+            got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
+            np.testing.assert_array_equal(got, want, err_msg=algo)
+            idx2, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m, hint_ordered=True)
+        np.testing.assert_array_equal(idx2.cpu().numpy(), want, err_msg=algo)
         np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
-    monkeypatch.setenv("SPC_FPS_CULL", "0")
-    np.testing.assert_array_equal(ext.furthest_point_sampling(cu(xyz), m).cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("cluster", [2, 4, 8])
-def test_fps_culled_every_cluster_size(ext, cluster, mode):
-    from spacap3d_b200 import _lib
-    xyz, m = cases.fps_large_cases()["clusters_20000"]
-    want = oracle.furthest_point_sampling(xyz, m)
-    _lib.call("spc_set_fps_cluster", cluster)
-    _lib.call("spc_set_fps_cull", mode)
-    try:
-        got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
-    finally:
-        _lib.call("spc_set_fps_cluster", 0)
-        _lib.call("spc_set_fps_cull", 0)
-    np.testing.assert_array_equal(got, want)
-
-
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
-def test_fps_strict_sequence_flags_and_chain(ext, mode):
-    """spc_furthest_point_sampling_ex2: the culled kernels report per scene whether every pick was a strict
-    unique maximum; the next samplers use that instead of the proof kernels.  Whatever the flags say, every
-    level of the 40k -> 2048 -> 1024 -> 512 -> 256 chain equals the oracle; a clean scene must be flagged 1 by
-    the culled kernels (so the shortcut is really exercised), scenes with exact ties 0."""
-    from spacap3d_b200 import _lib
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fps_strict_sequence_flags_and_chain(ext, algo):
+    """spc_furthest_point_sampling_ex2: per scene "the output is a strict FPS sequence" flags (1 only when proven
+    by the ordered-prefix check) feed the next sampler, which then skips proof and rounds.  Whatever the flags
+    say, every level of the 40k -> 2048 -> 1024 -> 512 -> 256 chain equals the oracle, and a flag of 1 is a promise
+    that FPS over a prefix of that output is the identity."""
     sc, _ = cases.fps_cases()["scene_40k"]                        # scene 1 has duplicated points
     lat = cases.fps_large_cases()["lattice_13824"][0][:1]          # exact ties everywhere
-    _lib.call("spc_set_fps_cull", mode)
-    try:
-        for xyz, expect in ((sc, [1, 0]), (lat, [0])):
+    with _algo(ext, algo):
+        for xyz in (sc, lat):
             cur_np, cur = xyz, cu(xyz)
             known, hint = None, False
             for lvl, m in enumerate((2048, 1024, 512, 256)):
@@ -100,14 +90,12 @@ def test_fps_strict_sequence_flags_and_chain(ext, mode):
                 np.testing.assert_array_equal(new_xyz.cpu().numpy(), cur_np)
                 flags = strict.cpu().numpy().tolist()
                 if lvl == 0:
-                    assert flags == (expect if mode else [0] * len(expect)), (mode, flags)
+                    assert flags == [0] * len(flags)             # no proof ran: unknown
                 for b, f in enumerate(flags):                     # a flag of 1 is a promise: identity below
                     if f and m // 2 >= 1:
                         sub_idx = oracle.furthest_point_sampling(cur_np[b:b + 1], m // 2)
                         np.testing.assert_array_equal(sub_idx[0], np.arange(m // 2))
                 cur, known, hint = new_xyz, strict, True
-    finally:
-        _lib.call("spc_set_fps_cull", 0)
 
 
 def test_fps_config5_200k_points(ext):
@@ -120,32 +108,69 @@ def test_fps_config5_200k_points(ext):
     np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, 8192))
 
 
-def test_fps_culled_scene_40k(ext):
-    """The BASELINE shape through the culled kernel (the path the graph pipeline uses)."""
-    from spacap3d_b200 import _lib
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fps_scene_40k_every_sampler(ext, ref_ext, algo):
+    """The BASELINE shape (8 x 40 000 -> 2048 is what the detector runs) through every sampler."""
     xyz, m = cases.fps_cases()["scene_40k"]
     want = oracle.furthest_point_sampling(xyz, m)
-    for mode in (1, 2, 3):
-        _lib.call("spc_set_fps_cull", mode)
-        try:
-            got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
-        finally:
-            _lib.call("spc_set_fps_cull", 0)
-        np.testing.assert_array_equal(got.cpu().numpy(), want)
-        np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
+    with _algo(ext, algo):
+        got, new_xyz = ext.furthest_point_sampling_with_xyz(cu(xyz), m)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(new_xyz.cpu().numpy(), cases.fps_follow_on(xyz, want, m))
+    if ref_ext is not None:
+        np.testing.assert_array_equal(want, ref_ext.furthest_point_sampling(cu(xyz), m).cpu().numpy())
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-def test_fps_every_cluster_size(ext, cluster, monkeypatch):
-    """Same indices whatever the cluster size (the tie-break order must not depend on it)."""
-    monkeypatch.setenv("SPC_FPS_CLUSTER", str(cluster))
+@pytest.mark.parametrize("algo", ALGOS)
+def test_fps_heavy_duplicates_every_sampler(ext, algo):
+    """12 000 points drawn with replacement from 5 000: every distance tie of the reference's block-tree arg-max
+    must be broken the same way, whatever the sampler and its internal layout."""
     rng = np.random.default_rng(7)
     base = rng.uniform(-3, 3, (3, 5000, 3)).astype(np.float32)
     pick = rng.integers(0, 5000, (3, 12000))
     xyz = np.ascontiguousarray(np.take_along_axis(base, pick[..., None].repeat(3, -1), 1))
     want = oracle.furthest_point_sampling(xyz, 700)
-    got = ext.furthest_point_sampling(cu(xyz), 700).cpu().numpy()
+    with _algo(ext, algo):
+        got = ext.furthest_point_sampling(cu(xyz), 700).cpu().numpy()
     np.testing.assert_array_equal(got, want)
+
+
+def test_fps_bucket_sampler_out_of_range(ext):
+    """SPC_FPS_BUCKET outside its size range is refused (SPC_ERR_UNSUPPORTED), never silently replaced."""
+    from spacap3d_b200 import _lib
+    xyz = cu(np.random.default_rng(0).uniform(-1, 1, (1, 50000, 3)).astype(np.float32))
+    with _algo(ext, "bucket"), pytest.raises(_lib.SpcUnsupported):
+        ext.furthest_point_sampling(xyz, 64)
+
+
+def test_launch_options_are_thread_local(ext):
+    """SURVEY 8b threading row (nn.DataParallel calls the library from several threads): launch hints are per
+    thread and per call; two threads using different samplers concurrently get the same, correct picks."""
+    import threading
+    xyz, m = cases.fps_large_cases()["clusters_20000"]
+    want = oracle.furthest_point_sampling(xyz, m)
+    x = cu(xyz)
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(algo, reps):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream), _algo(ext, algo):
+                for _ in range(reps):
+                    assert ext._options.fps_algo == {"cluster": ext.FPS_CLUSTER, "bucket": ext.FPS_BUCKET}[algo]
+                    got = ext.furthest_point_sampling(x, m)
+                    np.testing.assert_array_equal(got.cpu().numpy(), want)
+        except Exception as e:  # noqa: BLE001
+            errors.append((algo, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(a, 4)) for a in ("cluster", "bucket", "cluster", "bucket")]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert ext._options.fps_algo == ext.FPS_AUTO              # the main thread's options were never touched
 
 
 def test_fps_prefix_property(ext):

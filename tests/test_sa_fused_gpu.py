@@ -1,7 +1,7 @@
 """Fused set-abstraction kernel (tcgen05) against
-  (a) a torch emulation that applies the SAME bf16 roundings (tight: catches layout bugs), and
+  (a) a torch emulation that applies the SAME fp16 roundings (tight: catches layout bugs), and
   (b) the reference op sequence in fp32 (FAST_PATHS off, TF32 off) at the tolerance north_star
-      states for the bf16 MLP: rtol 1e-2 (measured against the tensor's max magnitude).
+      states for the fp16 MLP: rtol 1e-2 (measured against the tensor's max magnitude).
 Shapes are the five SA layers of SpaCap3D (widths, nsample and radii exact, batch/points reduced)."""
 import numpy as np
 import pytest
@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+HALF = torch.float16          # spacap3d_b200._ext.HALF: storage type of the fused kernel's operands
 
 # name: (n, Cf, npoint, radius, nsample, mlp)
 LAYERS = {
@@ -66,15 +67,19 @@ def test_fused_matches_reference_sequence(name):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     assert torch.equal(inds, ref_inds) and torch.equal(new_xyz, ref_xyz)      # indices bit-exact
     assert new_feat.shape == ref_feat.shape == (2, mlp[-1], npoint)
+    # north_star: "1e-2 for bf16 MLP" -- checked ELEMENT-WISE: |err| <= 1e-2 |ref| + 1e-2 rms(ref) everywhere
+    # (the kernel computes in fp16 with fp32 accumulation, ~8x tighter than bf16: measured 1-3e-3)
+    rms = ref_feat.pow(2).mean().sqrt()
+    nerr = ((new_feat - ref_feat).abs() / (ref_feat.abs() + rms)).max().item()
+    assert nerr <= 1e-2, (name, nerr)
     scale = ref_feat.abs().max().item()
-    err = (new_feat - ref_feat).abs().max().item()
-    assert err <= 1e-2 * scale, (name, err, scale)                              # bf16 MLP: rtol 1e-2
-    assert (new_feat - ref_feat).abs().mean().item() <= 2e-3 * scale
+    assert (new_feat - ref_feat).abs().max().item() <= 2.5e-3 * scale, name
+    assert (new_feat - ref_feat).abs().mean().item() <= 3e-4 * scale
 
 
 @pytest.mark.parametrize("name", ["sa1_xyz_height", "sa2", "sa3", "vote_agg"])
 def test_fused_matches_bf16_emulation(name):
-    """Same roundings as the kernel (bf16 h1/h2/W1/W2, fp32 accumulate) => agreement to ~1e-3."""
+    """Same roundings as the kernel (fp16 h1/h2/W1/W2, fp32 accumulate) => agreement to ~1e-3."""
     from spacap3d_b200 import _ext, pointnet2_modules as M, pointnet2_utils as U
     n, Cf, npoint, radius, nsample, mlp = LAYERS[name]
     m = _module(mlp, npoint, radius, nsample, seed=5)
@@ -87,21 +92,21 @@ def test_fused_matches_bf16_emulation(name):
         gx = (gx - new_xyz.transpose(1, 2).unsqueeze(-1)) / radius
         x = gx if feats is None else torch.cat([gx, U.grouping_operation(feats, idx)], 1)   # (B,K0,np,ns)
         if Cf > M.INLINE_MAX_FEATURES:
-            # projected form: the per-point feature projection is a bf16 GEMM output (bf16 inputs,
-            # fp32 accumulate, bf16 result); the xyz columns and the bias stay in fp32
-            fb = feats.to(torch.bfloat16).float()
-            G = torch.einsum("ok,bkn->bon", W0[:, 3:].to(torch.bfloat16).float(), fb).to(torch.bfloat16).float()
+            # projected form: the per-point feature projection is a fp16 GEMM output (fp16 inputs,
+            # fp32 accumulate, fp16 result); the xyz columns and the bias stay in fp32
+            fb = feats.to(HALF).float()
+            G = torch.einsum("ok,bkn->bon", W0[:, 3:].to(HALF).float(), fb).to(HALF).float()
             Gg = U.grouping_operation(G.contiguous(), idx)
             h1 = torch.relu(Gg + torch.einsum("ok,bkps->bops", W0[:, :3], gx) + b0[None, :, None, None])
         else:
             h1 = torch.relu(torch.einsum("ok,bkps->bops", W0, x) + b0[None, :, None, None])
-        h1 = h1.to(torch.bfloat16).float()
+        h1 = h1.to(HALF).float()
         h2 = torch.relu(torch.einsum("ok,bkps->bops", W1.float(), h1) + b1[None, :, None, None])
-        h2 = h2.to(torch.bfloat16).float()
+        h2 = h2.to(HALF).float()
         h3 = torch.einsum("ok,bkps->bops", W2.float(), h2)
         want = torch.relu(h3.max(-1).values + b2[None, :, None])
     scale = want.abs().max().item()
-    assert (got - want).abs().max().item() <= 6e-3 * scale, name
+    assert (got - want).abs().max().item() <= 1e-3 * scale, name
 
 
 def test_fused_not_used_in_training_or_with_grad():
