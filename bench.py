@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 
 N_POINTS = 40000
 REPEATS = 15             # the K-step timed region is repeated this often; the median region is reported
-N_STREAMS = 16           # CUDA-graph replay streams (batches are independent; FPS uses 64 of 148 SMs)
+N_STREAMS = 32           # CUDA-graph replay streams (batches in flight; the sampler is latency-bound, 4 ms per call)
 L2_BYTES = 126e6
 
 CONFIGS = {

@@ -56,14 +56,16 @@ int spc_furthest_point_sampling(const float *xyz, int B, int N, int npoint, int3
 size_t spc_fps_workspace_bytes(int B, int N, int npoint);
 /* Sampler selection, PER CALL (spc_furthest_point_sampling_ex2; the library keeps no mutable state).  Results are
  * identical for every choice.
- *   SPC_FPS_AUTO     the library decides: the bucketed sampler for 4096 <= N <= 40960 when a workspace is given,
- *                    otherwise the cluster sampler (small clouds: a single CTA).
+ *   SPC_FPS_AUTO     the library decides for a call that runs alone: the cluster sampler (small clouds: a single
+ *                    CTA), the lowest latency.
  *   SPC_FPS_CLUSTER  one thread-block cluster per scene; coordinates and running min-distances of every point in
  *                    registers / distributed shared memory, per-round arg-max over warp shuffles + DSMEM
  *                    (needs no workspace; holds 4 SMs per 40 k-point scene while it runs).
- *   SPC_FPS_BUCKET   one 256-thread CTA per scene; Morton-sorted points parked in L2 (workspace), per-bucket
- *                    bounding boxes and candidates in shared memory, only the buckets a new centre can change are
- *                    updated (four scenes share an SM).  SPC_ERR_UNSUPPORTED outside its size range. */
+ *   SPC_FPS_BUCKET   one 256-thread CTA per scene; Hilbert-sorted points parked in L2 (workspace), per-bucket
+ *                    bounding boxes and candidates on chip, only the buckets a new centre can change are updated
+ *                    (four scenes share an SM; ~3x the latency of the cluster sampler, ~1/15 of its SM-time: the
+ *                    choice for pipelines with several batches in flight).  Needs a workspace and
+ *                    4096 <= N <= 40960, else SPC_ERR_UNSUPPORTED. */
 #define SPC_FPS_AUTO 0
 #define SPC_FPS_CLUSTER 1
 #define SPC_FPS_BUCKET 2

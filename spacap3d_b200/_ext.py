@@ -49,6 +49,7 @@ def _stream():
 FPS_WORKSPACE_MIN_N = 4096
 
 FPS_AUTO, FPS_CLUSTER, FPS_BUCKET = 0, 1, 2      # include/spacap3d_ops.h SPC_FPS_*
+FPS_BUCKET_MIN_N, FPS_BUCKET_MAX_N = 4096, 40960  # size range of the bucketed sampler
 
 
 class _LaunchOptions(threading.local):
@@ -82,6 +83,15 @@ class launch_options:
             setattr(_options, k, v)
 
 
+def _fps_algo(N):
+    """The thread's sampler preference for a cloud of N points: a preference for the bucketed sampler only applies
+    inside its size range (a forward samples clouds of 40 000, 2 048, 1 024 ... points under one setting)."""
+    a = int(_options.fps_algo)
+    if a == FPS_BUCKET and not FPS_BUCKET_MIN_N <= N <= FPS_BUCKET_MAX_N:
+        return FPS_AUTO
+    return a
+
+
 def furthest_point_sampling(points, nsamples):
     """(B,N,3) f32 -> (B,nsamples) i32.   sampling.cpp:66-87"""
     _check(points, "points", torch.float32)
@@ -93,7 +103,7 @@ def furthest_point_sampling(points, nsamples):
             nbytes = _lib.load().spc_fps_workspace_bytes(B, N, int(nsamples))
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
             _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples),
-                      out.data_ptr(), None, 0, None, None, ws.data_ptr(), nbytes, int(_options.fps_algo), _stream())
+                      out.data_ptr(), None, 0, None, None, ws.data_ptr(), nbytes, _fps_algo(N), _stream())
         else:
             _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), None, _stream())
@@ -129,7 +139,7 @@ def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False, known
                       new_xyz.data_ptr(), int(bool(hint_ordered) and 2 <= nsamples <= N),
                       known_ordered.data_ptr() if known_ordered is not None else None,
                       strict.data_ptr() if strict is not None else None, ws.data_ptr(), nbytes,
-                      int(_options.fps_algo), _stream())
+                      _fps_algo(N), _stream())
         return (out, new_xyz, strict) if want_strict else (out, new_xyz)
     with torch.cuda.device(points.device):
         if (hint_ordered and 2 <= nsamples <= N) or (N >= FPS_WORKSPACE_MIN_N and nsamples >= 2):
@@ -137,7 +147,7 @@ def furthest_point_sampling_with_xyz(points, nsamples, hint_ordered=False, known
             ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=points.device)
             _lib.call("spc_furthest_point_sampling_ex2", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), new_xyz.data_ptr(), int(bool(hint_ordered)), None, None, ws.data_ptr(), nbytes,
-                      int(_options.fps_algo), _stream())
+                      _fps_algo(N), _stream())
         else:
             _lib.call("spc_furthest_point_sampling", points.data_ptr(), B, N, int(nsamples),
                       out.data_ptr(), new_xyz.data_ptr(), _stream())

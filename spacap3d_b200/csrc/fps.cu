@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1)) fps_cluster
 // Morton sort (prepass of the bucketed sampler below): spatially compact runs of consecutive points.
 // ================================================================================================
 constexpr int FMS_THREADS = 1024;
-constexpr int FMS_BINS = 32768;       // 32^3 Morton cells
+constexpr int FMS_BINS = 32768;       // 32^3 cells
 
 __device__ __forceinline__ unsigned morton_spread5(unsigned x) {   // 5 bits -> every third bit
   x = (x | (x << 8)) & 0x0000100Fu;
@@ -293,7 +293,31 @@ __device__ __forceinline__ unsigned morton_spread5(unsigned x) {   // 5 bits -> 
   return x;
 }
 
-// one CTA per scene: bounding box -> 15-bit Morton cell per point -> counting sort -> perm[b][N].
+// Position of cell (x, y, z) of a 32^3 grid along the 3-D Hilbert curve (Skilling's transpose algorithm, 5 bits per
+// axis).  Unlike the Z-order curve it has no long jumps, so a run of consecutive sorted points is always a spatially
+// connected blob: bounding boxes of 64-point runs are ~1/3 tighter (10.4 instead of 15.5 buckets touched per FPS
+// round on a 40 k-point room).  Any order gives the same picks; this one gives the fewest bucket visits.
+__device__ __forceinline__ unsigned hilbert15(unsigned x0, unsigned x1, unsigned x2) {
+  unsigned X[3] = {x0, x1, x2};
+#pragma unroll
+  for (unsigned Q = 16; Q > 1; Q >>= 1) {
+    const unsigned P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (X[i] & Q) X[0] ^= P;
+      else { const unsigned t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+    }
+  }
+  X[1] ^= X[0];
+  X[2] ^= X[1];
+  unsigned t = 0;
+#pragma unroll
+  for (unsigned Q = 16; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (morton_spread5(X[0]) << 2) | (morton_spread5(X[1]) << 1) | morton_spread5(X[2]);
+}
+
+// one CTA per scene: bounding box -> 15-bit Hilbert cell per point -> counting sort -> perm[b][N].
 // N <= FMS_THREADS * FMS_ITEMS (the culled kernel's own capacity); every thread keeps the cell codes of
 // its <= 40 points in registers (two per register) between the counting and the scatter pass, and
 // loads are issued eight points at a time so that the three passes are not latency-bound.
@@ -359,7 +383,7 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
       const unsigned qx = (unsigned)min(31, max(0, (int)((v[i][0] - bx) * gx)));
       const unsigned qy = (unsigned)min(31, max(0, (int)((v[i][1] - by) * gy)));
       const unsigned qz = (unsigned)min(31, max(0, (int)((v[i][2] - bz) * gz)));
-      const unsigned code = morton_spread5(qx) | (morton_spread5(qy) << 1) | (morton_spread5(qz) << 2);
+      const unsigned code = hilbert15(qx, qy, qz);
       if (k < N) atomicAdd(&s_cnt[code], 1);
       if ((i & 1) == 0) codes[(i0 + i) >> 1] = code;
       else codes[(i0 + i) >> 1] |= code << 16;
@@ -396,13 +420,6 @@ __global__ void __launch_bounds__(FMS_THREADS) fps_morton_sort_kernel(const floa
   }
 }
 
-// Several lanes hold the maximal key: the smallest virtual index wins.  Deliberately NOT inlined: ptxas
-// otherwise if-converts the rare path into predicated redux that sit on every round's dependency chain.
-__device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned lane) {
-  const unsigned vmin = __reduce_min_sync(0xffffffffu, hit ? v : 0xffffffffu);
-  return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
-}
-
 // ================================================================================================
 // Bucketed sampler: ONE small CTA per scene, points parked in L2.
 //
@@ -426,7 +443,6 @@ __device__ __noinline__ unsigned fps_resolve_tie(bool hit, unsigned v, unsigned 
 // share an SM.  Same arithmetic as everywhere else (sqdist_ref, fminf, strict tie-break on the reference's
 // virtual index), so the picks are bit-identical.
 // ================================================================================================
-constexpr int FB_THREADS = 256;
 constexpr unsigned FB_KEY_INIT = 0x501502F9u + 1u;      // __float_as_uint(1e10f) + 1
 
 __device__ __forceinline__ unsigned fb_v_of_k(unsigned k, int T, int log2T, int Q) {
@@ -482,156 +498,218 @@ __global__ void __launch_bounds__(256) fps_bucket_build_kernel(const float *__re
   if (lane < 6) boxes_all[((size_t)scene * NB + b) * 6 + lane] = lane < 3 ? lo[lane] : hi[lane - 3];
 }
 
-template <int BS, int U>
-__global__ void __launch_bounds__(FB_THREADS, 4)
-fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict__ kk_all,
-                  const float *__restrict__ boxes_all, int NB) {
-  constexpr int NW = FB_THREADS / 32;
-  constexpr int PPL = BS / 32;                        // points per lane and bucket
-  extern __shared__ __align__(16) unsigned char fb_smem[];
-  float4 *s_kxyz = reinterpret_cast<float4 *>(fb_smem);            // [NB] candidate: (k bits, x, y, z)
-  float4 *s_box4 = s_kxyz + NB;                                    // [NB] (lox, loy, loz, hix)
-  float2 *s_box2 = reinterpret_cast<float2 *>(s_box4 + NB);        // [NB] (hiy, hiz)
-  uint2 *s_keyv = reinterpret_cast<uint2 *>(s_box2 + NB);          // [NB] candidate: (key, v); key 0 = nothing selectable
-  uint16_t *s_list = reinterpret_cast<uint16_t *>(s_keyv + NB);    // [NB] touched buckets of the round
-  __shared__ uint4 s_wc[NW];                                       // per-warp (key, v, bucket)
-  __shared__ int s_cnt;
+// Equal keys: does point ka come before point kb in the reference's tie-break order?  Out of line: ties are rare
+// and their arithmetic must not sit in every round's instruction stream.
+__device__ __noinline__ bool fb_tie_before(int ka, int kb, int T, int log2T, int Q) {
+  return fb_v_of_k((unsigned)ka, T, log2T, Q) < fb_v_of_k((unsigned)kb, T, log2T, Q);
+}
+// Several lanes hold the maximal key: lane of the smallest virtual index.
+__device__ __noinline__ unsigned fb_resolve_tie(bool hit, int k, unsigned lane, int T, int log2T, int Q) {
+  const unsigned v = hit ? fb_v_of_k((unsigned)k, T, log2T, Q) : 0xffffffffu;
+  const unsigned vmin = __reduce_min_sync(0xffffffffu, v);
+  return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
+}
 
-  const int scene = blockIdx.x;
-  const int tid = threadIdx.x;
-  const unsigned lane = tid & 31u, warp = tid >> 5;
+__host__ __device__ constexpr size_t fb_smem_per_scene(int NB, int W, int S) {
+  return (size_t)((NB + 1) & ~1) * 40 + (size_t)W * 64 + (((size_t)W * 32 * S * 2 + 15) & ~(size_t)15);
+}
+
+// W warps work on one scene, G scenes share a CTA (W * G * 32 threads; the scenes of a CTA only share the SM, they
+// synchronise on separate named barriers).  Bucket b belongs to warp b % W, lane (b / W) % 32, slot (b / W) / 32:
+// every lane keeps the candidate key of its <= S buckets in registers, so the cull test and the arg-max read no
+// shared memory but the boxes, and spatial neighbours (consecutive buckets) land in different warps.
+template <int BS, int W, int G, int S>
+__global__ void __launch_bounds__(W * G * 32, G == 1 ? 4 : 1)
+fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict__ kk_all,
+                  const float *__restrict__ boxes_all, int NB, int B) {
+  constexpr int PPL = BS / 32;                        // points per lane and bucket
+  constexpr int QCAP = 32 * S;                        // a warp owns at most this many buckets
+  extern __shared__ __align__(16) unsigned char fb_smem[];
+  const int grp = threadIdx.x / (W * 32);             // scene slot of this CTA
+  const int scene = blockIdx.x * G + grp;
+  if (scene >= B) return;                             // whole scene groups leave; they own their barrier
+  const int t = threadIdx.x - grp * (W * 32);
+  const unsigned lane = t & 31u, w = t >> 5;
+  // per scene: candidate coordinates [NB] float4 (k bits, x, y, z), boxes [NB] float4 + float2, per-warp queues,
+  // per-warp candidates (double buffered)
+  const int NBe = (NB + 1) & ~1;                      // even, keeps every array 16-byte aligned
+  unsigned char *base = fb_smem + (size_t)grp * fb_smem_per_scene(NB, W, S);
+  float4 *s_kxyz = reinterpret_cast<float4 *>(base);
+  float4 *s_box4 = s_kxyz + NBe;
+  float2 *s_box2 = reinterpret_cast<float2 *>(s_box4 + NBe);
+  uint4 *s_wc = reinterpret_cast<uint4 *>(s_box2 + NBe);           // [2][W] x 2 uint4: (key, k, -, -), (k, x, y, z)
+  uint16_t *s_q = reinterpret_cast<uint16_t *>(s_wc + 4 * W) + w * QCAP;
+
   const float *xyz = p.xyz + (size_t)scene * p.N * 3;
   if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {       // verified shortcut, as in fps_cluster_kernel
-    if (tid == 0 && p.strict_out) p.strict_out[scene] = 1;
+    if (t == 0 && p.strict_out) p.strict_out[scene] = 1;
     int32_t *oidx = p.idx + (size_t)scene * p.npoint;
-    for (int j = tid; j < p.npoint; j += FB_THREADS) oidx[j] = j;
+    for (int j = t; j < p.npoint; j += W * 32) oidx[j] = j;
     if (p.new_xyz) {
       float *o = p.new_xyz + (size_t)scene * p.npoint * 3;
-      for (int e = tid; e < 3 * p.npoint; e += FB_THREADS) o[e] = __ldg(xyz + e);
+      for (int e = t; e < 3 * p.npoint; e += W * 32) o[e] = __ldg(xyz + e);
     }
     return;
   }
   float4 *pts = pts_all + (size_t)scene * NB * BS;
   const int32_t *kk = kk_all + (size_t)scene * NB * BS;
   const float *boxes = boxes_all + (size_t)scene * NB * 6;
-  for (int b = tid; b < NB; b += FB_THREADS) {
-    const float lx = __ldg(boxes + 6 * b + 0), ly = __ldg(boxes + 6 * b + 1), lz = __ldg(boxes + 6 * b + 2);
-    const float hx = __ldg(boxes + 6 * b + 3), hy = __ldg(boxes + 6 * b + 4), hz = __ldg(boxes + 6 * b + 5);
-    s_box4[b] = make_float4(lx, ly, lz, hx);
-    s_box2[b] = make_float2(hy, hz);
-    s_keyv[b] = make_uint2(hx >= lx ? FB_KEY_INIT : 0u, 0xffffffffu);   // every min-distance starts at 1e10
-    s_kxyz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned key[S];                                    // candidate key of my buckets; 0 = nothing selectable
+  // "Every pick so far was the strict unique maximum" (p.strict_out): then FPS over any prefix of the OUTPUT is the
+  // identity and the next set-abstraction layers skip their sampling without the proof kernels.  Every candidate
+  // carries one bit "another point holds the same key" up the three arg-max levels; only the winner's bit counts.
+  unsigned tiebits = 0u;                              // bit s: the candidate of my bucket in slot s is tied
+  bool strict = true;                                 // uniform over the scene's threads
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int b = (s * 32 + (int)lane) * W + (int)w;
+    key[s] = 0u;
+    if (b < NB) {
+      const float lx = __ldg(boxes + 6 * b + 0), ly = __ldg(boxes + 6 * b + 1), lz = __ldg(boxes + 6 * b + 2);
+      const float hx = __ldg(boxes + 6 * b + 3), hy = __ldg(boxes + 6 * b + 4), hz = __ldg(boxes + 6 * b + 5);
+      s_box4[b] = make_float4(lx, ly, lz, hx);
+      s_box2[b] = make_float2(hy, hz);
+      s_kxyz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      key[s] = hx >= lx ? FB_KEY_INIT : 0u;           // every min-distance starts at 1e10
+    }
   }
-  if (tid == 0) s_cnt = 0;
   const float p0x = __ldg(xyz + 0), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float ox = p0x, oy = p0y, oz = p0z;
   int32_t *idx = p.idx + (size_t)scene * p.npoint;
   float *nxyz = p.new_xyz ? p.new_xyz + (size_t)scene * p.npoint * 3 : nullptr;
-  const bool writer = tid == FB_THREADS - 1;
+  const bool writer = t == W * 32 - 1;
   if (writer) {
     idx[0] = 0;
     if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
-    if (p.strict_out) p.strict_out[scene] = 0;     // this kernel does not track ties: "unknown"
   }
-  __syncthreads();
-
-  // arg-max over the lanes holding (key, v): largest key, then smallest v (see fps_cull_kernel)
-  auto argmax_lane = [&](unsigned key, unsigned v, unsigned &kmax) -> unsigned {
-    kmax = __reduce_max_sync(0xffffffffu, key);
-    const bool hit = key == kmax;
-    const unsigned ties = __ballot_sync(0xffffffffu, hit);
-    unsigned src = __ffs(ties) - 1u;
-    if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fps_resolve_tie(hit, v, lane);   // rare
-    return src & 31u;
-  };
+  __syncwarp();
 
   for (int j = 1; j < p.npoint; ++j) {
-    // ---- 1. cull: which buckets can this centre change? -------------------------------------------
-    for (int b = tid; b < NB; b += FB_THREADS) {
-      const unsigned key = s_keyv[b].x;
-      if (key != 0u) {
-        const float4 b4 = s_box4[b];
-        const float2 b2 = s_box2[b];
-        const float ex = fmaxf(0.f, fmaxf(b4.x - ox, ox - b4.w)), ey = fmaxf(0.f, fmaxf(b4.y - oy, oy - b2.x)),
-                    ez = fmaxf(0.f, fmaxf(b4.z - oz, oz - b2.y));
-        const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;     // conservative w.r.t. fp32 rounding
-        if (lb2 < __uint_as_float(key - 1u)) s_list[atomicAdd(&s_cnt, 1)] = (uint16_t)b;
-      }
+    // ---- 1. cull my buckets: which of them can this centre change? --------------------------------
+    int nq = 0;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      // no branch around the test: the S slots are independent chains the scheduler can interleave
+      const int b = min((s * 32 + (int)lane) * W + (int)w, NB - 1);
+      const float4 b4 = s_box4[b];
+      const float2 b2 = s_box2[b];
+      const float ex = fmaxf(0.f, fmaxf(b4.x - ox, ox - b4.w)), ey = fmaxf(0.f, fmaxf(b4.y - oy, oy - b2.x)),
+                  ez = fmaxf(0.f, fmaxf(b4.z - oz, oz - b2.y));
+      const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;       // conservative w.r.t. fp32 rounding
+      const bool touch = key[s] != 0u && lb2 < __uint_as_float(key[s] - 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, touch);
+      if (touch) s_q[nq + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(s * 32 + (int)lane);
+      nq += __popc(m);
     }
-    __syncthreads();
-    const int n = s_cnt;
-    // ---- 2. update the touched buckets: warp per bucket, U buckets in flight per warp -------------
-    for (int e0 = (int)warp; e0 < n; e0 += NW * U) {
-      float4 pt[U][PPL];
-      int kq[U][PPL];
-      int bb[U];
+    __syncwarp();
+    // ---- 2. update the touched buckets (whole warp per bucket, the next bucket's loads in flight) ----
+    float4 pt[PPL], ptn[PPL];
+    int kq[PPL], kqn[PPL];
+    int sl = 0, sln = 0;
+    auto issue = [&](int e, float4 (&P)[PPL], int (&K)[PPL], int &slot) {
+      slot = (int)s_q[e];
+      const int b = slot * W + (int)w;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int e = e0 + u * NW;
-        bb[u] = e < n ? (int)s_list[e] : -1;
-        if (bb[u] >= 0) {
+      for (int q = 0; q < PPL; ++q) {
+        const int pos = b * BS + q * 32 + (int)lane;
+        P[q] = pts[pos];
+        K[q] = __ldg(kk + pos);
+      }
+    };
+    if (nq > 0) issue(0, ptn, kqn, sln);
+    for (int e = 0; e < nq; ++e) {
 #pragma unroll
-          for (int q = 0; q < PPL; ++q) {
-            const int pos = bb[u] * BS + q * 32 + (int)lane;
-            pt[u][q] = pts[pos];
-            kq[u][q] = __ldg(kk + pos);
-          }
+      for (int q = 0; q < PPL; ++q) { pt[q] = ptn[q]; kq[q] = kqn[q]; }
+      sl = sln;
+      if (e + 1 < nq) issue(e + 1, ptn, kqn, sln);
+      const int b = sl * W + (int)w;
+      unsigned bkey = 0u;
+      int bq = 0;
+      bool ltie = false;                              // my best key occurs twice among my own points
+#pragma unroll
+      for (int q = 0; q < PPL; ++q) {
+        const float t2 = fminf(sqdist_ref(pt[q].x, pt[q].y, pt[q].z, ox, oy, oz), pt[q].w);
+        if (t2 < pt[q].w) pts[b * BS + q * 32 + (int)lane].w = t2;
+        const unsigned kq_ = t2 < 0.f ? 0u : __float_as_uint(t2) + 1u;
+        if (kq_ > bkey) { bkey = kq_; bq = q; ltie = false; }
+        else if (q > 0 && kq_ == bkey && kq_ != 0u) {
+          ltie = true;
+          if (fb_tie_before(kq[q], kq[bq], p.T, p.log2T, p.Q)) bq = q;
         }
       }
+      float4 c = pt[0];
+      int ck = kq[0];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (bb[u] < 0) continue;                              // warp-uniform
-        unsigned bkey = 0u, bv = 0xffffffffu;
-        int bq = 0;
+      for (int q = 1; q < PPL; ++q) if (bq == q) { c = pt[q]; ck = kq[q]; }
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, bkey);
+      const bool hit = bkey == kmax;
+      const unsigned ties = __ballot_sync(0xffffffffu, hit);
+      unsigned src = __ffs(ties) - 1u;
+      if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fb_resolve_tie(hit, ck, lane, p.T, p.log2T, p.Q);
+      if (lane == src) s_kxyz[b] = make_float4(__int_as_float(ck), c.x, c.y, c.z);
+      const bool btie = (ties & (ties - 1u)) != 0u || __any_sync(0xffffffffu, hit && ltie);
+      const int owner = sl & 31, oslot = sl >> 5;
 #pragma unroll
-        for (int q = 0; q < PPL; ++q) {
-          const float4 v4 = pt[u][q];
-          const float t2 = fminf(sqdist_ref(v4.x, v4.y, v4.z, ox, oy, oz), v4.w);
-          if (t2 < v4.w) pts[bb[u] * BS + q * 32 + (int)lane].w = t2;
-          const unsigned key = t2 < 0.f ? 0u : __float_as_uint(t2) + 1u;
-          const unsigned v = fb_v_of_k((unsigned)kq[u][q], p.T, p.log2T, p.Q);
-          if (key > bkey || (key == bkey && key != 0u && v < bv)) { bkey = key; bv = v; bq = q; }
-        }
-        unsigned kmax;
-        const unsigned src = argmax_lane(bkey, bv, kmax);
-        if (lane == src) {
-          s_keyv[bb[u]] = make_uint2(kmax, bv);
-          float4 c = pt[u][0];
-          int ck = kq[u][0];
+      for (int s = 0; s < S; ++s)
+        if (s == oslot && (int)lane == owner) { key[s] = kmax; tiebits = btie ? (tiebits | (1u << s)) : (tiebits & ~(1u << s)); }
+    }
+    __syncwarp();
+    // ---- 3. select: my best bucket -> the warp's -> the scene's ------------------------------------
+    unsigned mkey = key[0];
+    int ms = 0;
+    bool mtie = false;                                // two of my buckets hold the same best key
 #pragma unroll
-          for (int q = 1; q < PPL; ++q) if (bq == q) { c = pt[u][q]; ck = kq[u][q]; }
-          s_kxyz[bb[u]] = make_float4(__int_as_float(ck), c.x, c.y, c.z);
-        }
+    for (int s = 1; s < S; ++s) {
+      if (key[s] > mkey) { mkey = key[s]; ms = s; mtie = false; }
+      else if (key[s] == mkey && mkey != 0u) {
+        mtie = true;
+        const int ba = (s * 32 + (int)lane) * W + (int)w, bb = (ms * 32 + (int)lane) * W + (int)w;
+        if (fb_tie_before(__float_as_int(s_kxyz[ba].x), __float_as_int(s_kxyz[bb].x), p.T, p.log2T, p.Q)) ms = s;
       }
     }
-    __syncthreads();
-    // ---- 3. select: arg-max over the bucket candidates ---------------------------------------------
-    if (tid == 0) s_cnt = 0;                                   // everybody has read n
-    unsigned mkey = 0u, mv = 0xffffffffu, mb = 0u;
-    for (int b = tid; b < NB; b += FB_THREADS) {
-      const uint2 kv = s_keyv[b];
-      if (kv.x > mkey || (kv.x == mkey && kv.x != 0u && kv.y < mv)) { mkey = kv.x; mv = kv.y; mb = (unsigned)b; }
+    mtie = mtie || ((tiebits >> ms) & 1u) != 0u;
+    const int mb = (ms * 32 + (int)lane) * W + (int)w;
+    const unsigned wmax = __reduce_max_sync(0xffffffffu, mkey);
+    {
+      const bool hit = mkey == wmax;
+      const unsigned ties = __ballot_sync(0xffffffffu, hit);
+      unsigned src = __ffs(ties) - 1u;
+      if (wmax != 0u && (ties & (ties - 1u)) != 0u)
+        src = fb_resolve_tie(hit, hit ? __float_as_int(s_kxyz[mb].x) : 0, lane, p.T, p.log2T, p.Q);
+      const bool wtie = (ties & (ties - 1u)) != 0u || __any_sync(0xffffffffu, hit && mtie);
+      if (lane == src) {
+        const float4 c = wmax != 0u ? s_kxyz[mb] : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 *dst = s_wc + ((j & 1) * W + (int)w) * 2;
+        dst[0] = make_uint4(wmax, __float_as_uint(c.x), wtie ? 1u : 0u, 0u);
+        dst[1] = make_uint4(__float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), __float_as_uint(c.w));
+      }
     }
-    unsigned wmax;
-    const unsigned wsrc = argmax_lane(mkey, mv, wmax);
-    if (lane == wsrc) s_wc[warp] = make_uint4(mkey, mv, mb, 0u);
-    __syncthreads();
-    uint4 c4 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-    if (lane < NW) c4 = s_wc[lane];
-    unsigned bmax;
-    const unsigned csrc = argmax_lane(c4.x, c4.y, bmax);
-    const unsigned wb = __shfl_sync(0xffffffffu, c4.z, csrc);
+    if (W > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(W * 32) : "memory");
+    else __syncwarp();
+    const uint4 *wc = s_wc + (j & 1) * W * 2;
+    uint4 c2 = make_uint4(0u, 0u, 0u, 0u);
+    if (lane < W) c2 = wc[lane * 2];
+    const unsigned bmax = __reduce_max_sync(0xffffffffu, c2.x);
+    unsigned csrc;
+    {
+      const bool hit = c2.x == bmax && lane < W;
+      const unsigned ties = __ballot_sync(0xffffffffu, hit);
+      csrc = __ffs(ties) - 1u;
+      if (bmax != 0u && (ties & (ties - 1u)) != 0u) csrc = fb_resolve_tie(hit, (int)c2.y, lane, p.T, p.log2T, p.Q);
+      strict = strict && bmax != 0u && (ties & (ties - 1u)) == 0u && !__any_sync(0xffffffffu, hit && c2.z != 0u);
+    }
     int old = 0;
     if (bmax == 0u) { ox = p0x; oy = p0y; oz = p0z; }
     else {
-      const float4 w = s_kxyz[wb];
-      old = __float_as_int(w.x); ox = w.y; oy = w.z; oz = w.w;
+      const uint4 c = wc[(csrc & 31u) * 2 + 1];
+      old = (int)c.x; ox = __uint_as_float(c.y); oy = __uint_as_float(c.z); oz = __uint_as_float(c.w);
     }
     if (writer) {
       idx[j] = old;
       if (nxyz) { nxyz[3 * j + 0] = ox; nxyz[3 * j + 1] = oy; nxyz[3 * j + 2] = oz; }
     }
   }
+  if (writer && p.strict_out) p.strict_out[scene] = strict ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -838,7 +916,22 @@ extern "C" int spc_furthest_point_sampling_ex2(const float *xyz, int B, int N, i
                   workspace_bytes, algo, stream_);
 }
 
-template <int BS, int U>
+template <int BS, int W, int G, int S>
+static int launch_fps_bucket_cfg(const FpsParams &p, int B, int NB, float4 *pts, const int32_t *kk, const float *boxes,
+                                 cudaStream_t stream) {
+  auto kern = fps_bucket_kernel<BS, W, G, S>;
+  const size_t smem = fb_smem_per_scene(NB, W, S) * G;
+  if (smem > 227 * 1024) {
+    set_error("fps: bucket table of %d entries x %d scenes does not fit in shared memory", NB, G);
+    return SPC_ERR_UNSUPPORTED;
+  }
+  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(B, G), W * G * 32, smem, stream>>>(p, pts, kk, boxes, NB, B);
+  SPC_LAUNCH_CHECK("fps_bucket_kernel");
+  return SPC_OK;
+}
+
+template <int BS>
 static int launch_fps_bucket(const FpsParams &p, int B, int N, int32_t *perm, void *ws_tail, cudaStream_t stream) {
   const int NB = (N + BS - 1) / BS;
   float4 *pts = reinterpret_cast<float4 *>(ws_tail);
@@ -850,12 +943,20 @@ static int launch_fps_bucket(const FpsParams &p, int B, int N, int32_t *perm, vo
   SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
   fps_bucket_build_kernel<BS><<<dim3(ceil_div(NB, 8), B), 256, 0, stream>>>(p.xyz, perm, N, NB, pts, kk, boxes);
   SPC_LAUNCH_CHECK("fps_bucket_build_kernel");
-  auto kern = fps_bucket_kernel<BS, U>;
-  const size_t smem = (size_t)NB * 50;
-  SPC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B, FB_THREADS, smem, stream>>>(p, pts, kk, boxes, NB);
-  SPC_LAUNCH_CHECK("fps_bucket_kernel");
-  return SPC_OK;
+  // 8 warps per scene, one scene per CTA.  Measured on B200 (8 x 40 k -> 2048): ms per call alone / k scenes per
+  // second with 32 sampler calls in flight / k scenes per second of the whole detector pipeline --
+  // W8 G1 4.0 / 39.6 / 16.4; W8 G2 4.9 / 42.8 / 16.4; W8 G4 7.0 / 33.7 / 14.2; W4 G8 8.3 / 26.8 / 12.5; W16 G1 3.9 / 32.6.
+  // The rounds are bound by dependent-instruction latency, so scenes packed onto one SM slow each other down, and
+  // the pipeline no longer gains from freeing SMs: with this sampler it is bound by the other kernels.
+  constexpr int W = 8;
+  const int S = ceil_div(ceil_div(NB, W), 32);
+  switch (S) {
+    case 1: return launch_fps_bucket_cfg<BS, W, 1, 1>(p, B, NB, pts, kk, boxes, stream);
+    case 2: return launch_fps_bucket_cfg<BS, W, 1, 2>(p, B, NB, pts, kk, boxes, stream);
+    case 3: return launch_fps_bucket_cfg<BS, W, 1, 3>(p, B, NB, pts, kk, boxes, stream);
+  }
+  set_error("fps: no bucket kernel for %d buckets", NB);
+  return SPC_ERR_UNSUPPORTED;
 }
 
 static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, float *new_xyz,
@@ -900,14 +1001,17 @@ static int fps_impl(const float *xyz, int B, int N, int npoint, int32_t *idx, fl
   }
   // ---- bucketed sampler (points parked in L2, one small CTA per scene): needs the caller's workspace -------
   const int BS = fb_bucket_size(N);
-  if (algo != SPC_FPS_CLUSTER && BS && workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) &&
+  // SPC_FPS_AUTO serves the single call: the cluster sampler finishes a 40 k-point scene in 1.25 ms, the bucketed one
+  // in 4 ms -- but it holds a quarter of an SM instead of four, which is what a pipeline with many batches in flight
+  // wants (spacap3d_b200/pipeline.py asks for it explicitly).
+  if (algo == SPC_FPS_BUCKET && BS && workspace && workspace_bytes >= spc_fps_workspace_bytes(B, N, npoint) &&
       npoint >= 2) {
     const size_t head = ((size_t)B * npoint + (size_t)B + (size_t)B * N) * 4;
     int32_t *perm = reinterpret_cast<int32_t *>(workspace) + (size_t)B * npoint + (size_t)B;
     void *tail = reinterpret_cast<char *>(workspace) + fb_align16(head);
     SPC_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "fps: workspace must be 16-byte aligned");
-    return BS == 32 ? launch_fps_bucket<32, 4>(p, B, N, perm, tail, stream)
-                    : launch_fps_bucket<64, 2>(p, B, N, perm, tail, stream);
+    return BS == 32 ? launch_fps_bucket<32>(p, B, N, perm, tail, stream)
+                    : launch_fps_bucket<64>(p, B, N, perm, tail, stream);
   }
   if (algo == SPC_FPS_BUCKET) {
     set_error("fps: SPC_FPS_BUCKET needs a workspace of spc_fps_workspace_bytes() and 4096 <= N <= %d (got N=%d)",

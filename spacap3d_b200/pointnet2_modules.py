@@ -34,9 +34,14 @@ def _sample_centres(xyz, npoint, inds=None):
         # one kernel: the FPS epilogue already holds the winners' coordinates.  Centres produced by
         # an FPS are tagged so that the next layer can try the verified "already FPS-ordered"
         # shortcut (exact: see spc_furthest_point_sampling_ex).
+        # `_spc_fps_strict` carries the producing call's per-scene "strict sequence" flags (tracked exactly by the
+        # bucketed sampler, implied by a successful proof): flagged scenes need neither the proof nor the rounds.
         hint = bool(getattr(xyz, "_spc_fps_ordered", False))
-        inds, new_xyz = _ext.furthest_point_sampling_with_xyz(xyz.contiguous(), npoint, hint_ordered=hint)
+        known = getattr(xyz, "_spc_fps_strict", None) if hint and npoint <= xyz.shape[1] else None
+        inds, new_xyz, strict = _ext.furthest_point_sampling_with_xyz(
+            xyz.contiguous(), npoint, hint_ordered=hint, known_ordered=known, want_strict=True)
         new_xyz._spc_fps_ordered = True
+        new_xyz._spc_fps_strict = strict
         return new_xyz, inds
     if inds is None:
         inds = pointnet2_utils.furthest_point_sample(xyz, npoint)

@@ -57,8 +57,6 @@ def test_fps_large_clouds(ext, name):
     xyz, m = cases.fps_large_cases()[name]
     want = oracle.furthest_point_sampling(xyz, m)
     for algo in ALGOS:
-        if algo == "bucket" and not 4096 <= xyz.shape[1] <= 40960:
-            continue                                   # outside the bucketed sampler's range (refused, see below)
         with _algo(ext, algo):
             got = ext.furthest_point_sampling(cu(xyz), m).cpu().numpy()
             np.testing.assert_array_equal(got, want, err_msg=algo)
@@ -69,14 +67,16 @@ def test_fps_large_clouds(ext, name):
 
 @pytest.mark.parametrize("algo", ALGOS)
 def test_fps_strict_sequence_flags_and_chain(ext, algo):
-    """spc_furthest_point_sampling_ex2: per scene "the output is a strict FPS sequence" flags (1 only when proven
-    by the ordered-prefix check) feed the next sampler, which then skips proof and rounds.  Whatever the flags
-    say, every level of the 40k -> 2048 -> 1024 -> 512 -> 256 chain equals the oracle, and a flag of 1 is a promise
-    that FPS over a prefix of that output is the identity."""
+    """spc_furthest_point_sampling_ex2: per scene "the output is a strict FPS sequence" flags (tracked exactly by the
+    bucketed sampler, implied by a successful ordered-prefix proof, 0 = unknown for the cluster sampler) feed the
+    next sampler, which then skips proof and rounds.  Whatever the flags say, every level of the
+    40k -> 2048 -> 1024 -> 512 -> 256 chain equals the oracle, and a flag of 1 is a promise that FPS over a prefix of
+    that output is the identity; a clean scene must be flagged 1 by the bucketed sampler (so the shortcut is really
+    exercised), scenes with exact ties 0."""
     sc, _ = cases.fps_cases()["scene_40k"]                        # scene 1 has duplicated points
     lat = cases.fps_large_cases()["lattice_13824"][0][:1]          # exact ties everywhere
     with _algo(ext, algo):
-        for xyz in (sc, lat):
+        for xyz, expect in ((sc, [1, 0]), (lat, [0])):
             cur_np, cur = xyz, cu(xyz)
             known, hint = None, False
             for lvl, m in enumerate((2048, 1024, 512, 256)):
@@ -90,7 +90,7 @@ def test_fps_strict_sequence_flags_and_chain(ext, algo):
                 np.testing.assert_array_equal(new_xyz.cpu().numpy(), cur_np)
                 flags = strict.cpu().numpy().tolist()
                 if lvl == 0:
-                    assert flags == [0] * len(flags)             # no proof ran: unknown
+                    assert flags == (expect if algo == "bucket" else [0] * len(expect)), (algo, flags)
                 for b, f in enumerate(flags):                     # a flag of 1 is a promise: identity below
                     if f and m // 2 >= 1:
                         sub_idx = oracle.furthest_point_sampling(cur_np[b:b + 1], m // 2)
@@ -136,11 +136,19 @@ def test_fps_heavy_duplicates_every_sampler(ext, algo):
 
 
 def test_fps_bucket_sampler_out_of_range(ext):
-    """SPC_FPS_BUCKET outside its size range is refused (SPC_ERR_UNSUPPORTED), never silently replaced."""
+    """C ABI: SPC_FPS_BUCKET outside its size range is refused (SPC_ERR_UNSUPPORTED), never silently replaced;
+    the Python wrapper treats the thread-local setting as a preference and applies it inside the range only."""
     from spacap3d_b200 import _lib
     xyz = cu(np.random.default_rng(0).uniform(-1, 1, (1, 50000, 3)).astype(np.float32))
-    with _algo(ext, "bucket"), pytest.raises(_lib.SpcUnsupported):
-        ext.furthest_point_sampling(xyz, 64)
+    out = torch.empty((1, 64), dtype=torch.int32, device=DEV)
+    nbytes = _lib.load().spc_fps_workspace_bytes(1, 50000, 64)
+    ws = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=DEV)
+    with pytest.raises(_lib.SpcUnsupported):
+        _lib.call("spc_furthest_point_sampling_ex2", xyz.data_ptr(), 1, 50000, 64, out.data_ptr(), None, 0, None, None,
+                  ws.data_ptr(), nbytes, ext.FPS_BUCKET, torch.cuda.current_stream().cuda_stream)
+    with _algo(ext, "bucket"):
+        got = ext.furthest_point_sampling(xyz, 64)
+    np.testing.assert_array_equal(got.cpu().numpy(), oracle.furthest_point_sampling(xyz.cpu().numpy(), 64))
 
 
 def test_launch_options_are_thread_local(ext):
