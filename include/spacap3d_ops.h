@@ -197,16 +197,34 @@ int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float 
                       const void *skip_pm_f16, int B, int n, int m, int C2, int C1, void *X_f16,
                       void *stream);
 
-/* Voting tail (models/voting_module.py:52-61 + models/SpaCapNet.py:66-67), vote_factor 1:
- * net (B*S,3+D) f32 = last voting conv WITHOUT bias, point-major; bias (3+D); seed_xyz (B,S,3);
- * seed_pm (B,S,D) FP16 -> vote_xyz (B,S,3), L2-normalised vote features channel-major f32 (B,D,S)
- * and point-major FP16 (B,S,D).  D <= 256. */
-int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz, const void *seed_pm_f16,
-                  int B, int S, int D, float *vote_xyz, float *vote_feat_cm, void *vote_pm_f16,
-                  void *stream);
+/* One 1x1-conv layer of the point-major eval path on tcgen05 tensor cores (csrc/pm_linear.cu): Y = act(X . W^T + b).
+ * Replaces the library GEMMs + layout / elementwise kernels of PointnetFPModule's SharedMLP
+ * (pointnet2_modules.py:412-421), VotingModule (models/voting_module.py:34-61, plus the L2 normalisation of
+ * models/SpaCapNet.py:66-67) and the proposal head (models/proposal_module.py:46-54,73).
+ *   X_hi (M,K) FP16 point-major rows, X_lo (M,K) FP16 or NULL (x = hi + lo);  K % 64 == 0
+ *   W_hi, W_lo (N,K) FP16: the BatchNorm-folded fp32 weights as a pair (w = hi + lo);  bias (N) f32;  N <= 272
+ *   three MMAs per product (hi.hi + lo.hi + hi.lo), fp32 accumulation: fp32-grade results
+ *   points_per_scene: rows per scene (M = B * points_per_scene), used by the channel-major outputs
+ * mode:
+ *   SPC_PM_HIDDEN    y = relu(.)            -> Y_hi, Y_lo (M,N) FP16 pair (the next layer's X);  N % 32 == 0
+ *   SPC_PM_OUT_CM    y = relu(.)            -> out (B,N,points) f32 channel-major (the reference's layout) and
+ *                                              Y_hi (and Y_lo if not NULL) (M,N) FP16 point-major;  N % 32 == 0
+ *   SPC_PM_OUT_PM32  y = .  (no activation) -> out (M,N) f32 point-major (proposal head scores)
+ *   SPC_PM_LINEAR    y = .  (no activation) -> Y_hi (and Y_lo if not NULL) (M,N) FP16 (the per-point projection G of
+ *                                              the fused set-abstraction kernel, conv0 hoisted out of the grouping)
+ *   SPC_PM_VOTE      net = . (N = D + 3; the caller moves conv3's three xyz-offset rows BEHIND its D feature
+ *                    rows; D % 32 == 0)     -> v = seed_cm (B,D,points) + net[0:D];  out (B,D,points) = v / ||v||_2,
+ *                                              Y_hi (and Y_lo) (M,D) the same point-major;
+ *                                              vote_xyz (B,points,3) = seed_xyz + net[D:D+3] */
+#define SPC_PM_HIDDEN 0
+#define SPC_PM_OUT_CM 1
+#define SPC_PM_OUT_PM32 2
+#define SPC_PM_VOTE 3
+#define SPC_PM_LINEAR 4
+int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, const void *W_hi, const void *W_lo,
+                  const float *bias, int N, int mode, int points_per_scene, void *Y_hi, void *Y_lo, float *out,
+                  const float *seed_cm, const float *seed_xyz, float *vote_xyz, void *stream);
 
-/* point-major FP16 (B,n,C) -> channel-major f32 (B,C,n) */
-int spc_pm_to_cm(const void *pm_f16, int B, int n, int C, float *cm, void *stream);
 
 /* ---- training-mode BatchNorm + ReLU of a shared-MLP block -------------------------------------------
  * Replaces nn.BatchNorm2d(training) + nn.ReLU(inplace=True) of the reference's Conv2d block

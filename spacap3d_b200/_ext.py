@@ -365,34 +365,65 @@ def interp_cat_pm(known_pm, idx, weight, skip_pm):
     return X
 
 
-def vote_tail(net, bias, seed_xyz, seed_pm):
-    """Voting tail: net (B*S,3+D) f32 (no bias), bias (3+D), seed_xyz (B,S,3), seed_pm (B,S,D) fp16 ->
-    vote_xyz (B,S,3), vote features L2-normalised: channel-major f32 (B,D,S) and point-major fp16 (B,S,D)."""
-    _check(net, "net", torch.float32)
+PM_HIDDEN, PM_OUT_CM, PM_OUT_PM32, PM_VOTE, PM_LINEAR = 0, 1, 2, 3, 4     # include/spacap3d_ops.h SPC_PM_*
+
+
+def split_half(w):
+    """fp32 tensor -> (hi, lo) fp16 pair with w ~= hi + lo to ~2^-22 (operands of spc_pm_linear)."""
+    hi = w.to(HALF)
+    lo = (w - hi.float()).to(HALF)
+    return hi.contiguous(), lo.contiguous()
+
+
+def pm_linear(X, W, bias, mode, points_per_scene, seed_cm=None, seed_xyz=None, want_lo=True):
+    """One point-major 1x1-conv layer on tcgen05 (spc_pm_linear).  X: (M,K) fp16 tensor or (hi, lo) pair;
+    W: (hi, lo) pair of (N,K) fp16; bias (N) f32.  Returns, by mode:
+      PM_HIDDEN    (Y_hi, Y_lo)                       relu, fp16 pair (M,N)
+      PM_OUT_CM    out (B,N,points) f32, (Y_hi, Y_lo) relu
+      PM_OUT_PM32  out (M,N) f32                      no activation
+      PM_VOTE      vote_xyz (B,points,3), out (B,D,points) f32 L2-normalised, (Y_hi, Y_lo) (M,D)
+      PM_LINEAR    (Y_hi, Y_lo)                       no activation, fp16 pair (M,N)"""
+    X_hi, X_lo = X if isinstance(X, (tuple, list)) else (X, None)
+    W_hi, W_lo = W
+    _check(X_hi, "X_hi", HALF)
+    _check(W_hi, "W_hi", HALF)
+    _check(W_lo, "W_lo", HALF)
     _check(bias, "bias", torch.float32)
-    _check(seed_xyz, "seed_xyz", torch.float32)
-    _check(seed_pm, "seed_pm", HALF)
-    _same_device(net, bias, seed_xyz, seed_pm)
-    B, S, D = seed_pm.shape
-    assert net.shape == (B * S, 3 + D) and bias.numel() == 3 + D
-    vote_xyz = torch.empty((B, S, 3), dtype=torch.float32, device=net.device)
-    cm = torch.empty((B, D, S), dtype=torch.float32, device=net.device)
-    pm = torch.empty((B, S, D), dtype=HALF, device=net.device)
-    with torch.cuda.device(net.device):
-        _lib.call("spc_vote_tail", net.data_ptr(), bias.data_ptr(), seed_xyz.data_ptr(), seed_pm.data_ptr(), B, S, D,
-                  vote_xyz.data_ptr(), cm.data_ptr(), pm.data_ptr(), _stream())
-    return vote_xyz, cm, pm
-
-
-def pm_to_cm(pm):
-    """(B,n,C) fp16 point-major -> (B,C,n) f32 channel-major."""
-    _check(pm, "pm", HALF)
-    _same_device(pm)
-    B, n, C = pm.shape
-    cm = torch.empty((B, C, n), dtype=torch.float32, device=pm.device)
-    with torch.cuda.device(pm.device):
-        _lib.call("spc_pm_to_cm", pm.data_ptr(), B, n, C, cm.data_ptr(), _stream())
-    return cm
+    _same_device(X_hi, W_hi, W_lo, bias)
+    if X_lo is not None:
+        _check(X_lo, "X_lo", HALF)
+        assert X_lo.shape == X_hi.shape
+    M, K = X_hi.shape
+    N = W_hi.shape[0]
+    assert W_hi.shape == (N, K) == W_lo.shape and bias.numel() == N and M % points_per_scene == 0
+    B, dev = M // points_per_scene, X_hi.device
+    Y_hi = Y_lo = out = vote_xyz = None
+    D = N - 3 if mode == PM_VOTE else N
+    if mode != PM_OUT_PM32:
+        Y_hi = torch.empty((M, D), dtype=HALF, device=dev)
+        Y_lo = torch.empty((M, D), dtype=HALF, device=dev) if want_lo else None
+    if mode == PM_OUT_CM:
+        out = torch.empty((B, N, points_per_scene), dtype=torch.float32, device=dev)
+    elif mode == PM_OUT_PM32:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    elif mode == PM_VOTE:
+        _check(seed_cm, "seed_cm", torch.float32)
+        _check(seed_xyz, "seed_xyz", torch.float32)
+        assert seed_cm.shape == (B, D, points_per_scene) and seed_xyz.shape == (B, points_per_scene, 3)
+        out = torch.empty((B, D, points_per_scene), dtype=torch.float32, device=dev)
+        vote_xyz = torch.empty((B, points_per_scene, 3), dtype=torch.float32, device=dev)
+    ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+    with torch.cuda.device(dev):
+        _lib.call("spc_pm_linear", X_hi.data_ptr(), ptr(X_lo), M, K, W_hi.data_ptr(), W_lo.data_ptr(), bias.data_ptr(),
+                  N, int(mode), int(points_per_scene), ptr(Y_hi), ptr(Y_lo), ptr(out), ptr(seed_cm), ptr(seed_xyz),
+                  ptr(vote_xyz), _stream())
+    if mode in (PM_HIDDEN, PM_LINEAR):
+        return Y_hi, Y_lo
+    if mode == PM_OUT_CM:
+        return out, (Y_hi, Y_lo)
+    if mode == PM_OUT_PM32:
+        return out
+    return vote_xyz, out, (Y_hi, Y_lo)
 
 
 def _bn_workspace(C, device):

@@ -1,5 +1,5 @@
 // fp_vote.cu -- small fused kernels around the point-major (fp16) eval path of the detector's
-// feature-propagation and voting stages.  They replace chains of tiny
+// feature-propagation stage; the 1x1 convs and the voting tail are csrc/pm_linear.cu.  They replace chains of tiny
 // ATen launches (sqrt/add/reciprocal/sum/div, cat, transpose copies, norm/div; ~18 % of the SM time
 // of a forward, profiles/r1_sm_cycles_per_kernel_one_forward.csv) with one kernel each.
 #include <cuda_fp16.h>
@@ -130,84 +130,6 @@ __global__ void __launch_bounds__(256) interp_cat_pm_kernel(const __half *__rest
   for (int c = lane; c < C1 / 8; c += 32) out[C2 / 8 + c] = __ldg(sk + c);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Voting tail (reference models/voting_module.py:52-61 + models/SpaCapNet.py:66-67), vote_factor 1:
-//   net (B*S, 3+D) fp32 = conv3 output WITHOUT bias (point-major), bias (3+D)
-//   vote_xyz[b,s,:]      = seed_xyz[b,s,:] + net[.,0:3] + bias[0:3]
-//   v                    = seed_feat[b,s,:] + net[.,3:] + bias[3:]
-//   vote_features[b,:,s] = v / ||v||_2          (channel-major fp32, the tensor the reference exposes)
-//   vote_pm[b,s,:]       = same, point-major fp16 (input of the vote-aggregation projection GEMM)
-// One CTA per 32 seeds: a warp normalises one seed at a time (lanes over channels), the tile is
-// transposed through shared memory so that the channel-major store is coalesced along seeds.
-// ------------------------------------------------------------------------------------------------
-constexpr int VT_SEEDS = 32;
-
-__global__ void __launch_bounds__(256) vote_tail_kernel(const float *__restrict__ net, const float *__restrict__ bias,
-                                                        const float *__restrict__ seed_xyz,
-                                                        const __half *__restrict__ seed_pm, int S, int D,
-                                                        float *__restrict__ vote_xyz,
-                                                        float *__restrict__ vote_feat_cm,
-                                                        __half *__restrict__ vote_pm) {
-  extern __shared__ float s_tile[];                  // [D][VT_SEEDS + 1]
-  const int b = blockIdx.y;
-  const int s0 = blockIdx.x * VT_SEEDS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ld = 3 + D;
-  for (int t = warp; t < VT_SEEDS; t += 8) {
-    const int s = s0 + t;
-    if (s >= S) break;                               // warp-uniform
-    const float *row = net + ((size_t)b * S + s) * ld;
-    if (lane < 3)
-      vote_xyz[((size_t)b * S + s) * 3 + lane] = __ldg(seed_xyz + ((size_t)b * S + s) * 3 + lane) + __ldg(row + lane) + __ldg(bias + lane);
-    const __half *sf = seed_pm + ((size_t)b * S + s) * D;
-    float v[8];                                      // D <= 256: channel c = lane + 32*i
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = c < D ? __half2float(sf[c]) + __ldg(row + 3 + c) + __ldg(bias + 3 + c) : 0.f;
-      ss = fmaf(v[i], v[i], ss);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float inv = 1.0f / sqrtf(ss);
-    __half *op = vote_pm + ((size_t)b * S + s) * D;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = lane + 32 * i;
-      if (c < D) {
-        const float r = v[i] * inv;
-        s_tile[c * (VT_SEEDS + 1) + t] = r;
-        op[c] = __float2half_rn(r);
-      }
-    }
-  }
-  __syncthreads();
-  const int nseed = min(VT_SEEDS, S - s0);
-  for (int e = threadIdx.x; e < D * VT_SEEDS; e += 256) {
-    const int c = e / VT_SEEDS, t = e - c * VT_SEEDS;
-    if (t < nseed) vote_feat_cm[((size_t)b * D + c) * S + s0 + t] = s_tile[c * (VT_SEEDS + 1) + t];
-  }
-}
-
-// point-major fp16 (B,n,C) -> channel-major fp32 (B,C,n)   (tile transpose through shared memory)
-__global__ void __launch_bounds__(256) pm_to_cm_kernel(const __half *__restrict__ pm, int n, int C,
-                                                       float *__restrict__ cm) {
-  __shared__ float t[32][33];
-  const int b = blockIdx.z;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int p = p0 + r, c = c0 + tx;
-    t[r][tx] = (p < n && c < C) ? __half2float(pm[((size_t)b * n + p) * C + c]) : 0.f;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r, p = p0 + tx;
-    if (c < C && p < n) cm[((size_t)b * C + c) * n + p] = t[tx][r];
-  }
-}
-
 }  // namespace spc
 
 using namespace spc;
@@ -236,31 +158,5 @@ extern "C" int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, c
       (const __half *)known_pm_f16, idx, weight, (const __half *)skip_pm_f16, n, m, C2, C1,
       (__half *)X_f16);
   SPC_LAUNCH_CHECK("interp_cat_pm_kernel");
-  return SPC_OK;
-}
-
-extern "C" int spc_vote_tail(const float *net, const float *bias, const float *seed_xyz,
-                             const void *seed_pm_f16, int B, int S, int D, float *vote_xyz,
-                             float *vote_feat_cm, void *vote_pm_f16, void *stream_) {
-  SPC_CHECK_ARG(B >= 0 && S >= 0 && D >= 1 && D <= 256, "vote_tail: feature dim must be in 1..256");
-  if (B == 0 || S == 0) return SPC_OK;
-  SPC_CHECK_ARG(net && bias && seed_xyz && seed_pm_f16 && vote_xyz && vote_feat_cm && vote_pm_f16, "vote_tail: null pointer");
-  SPC_CHECK_ARG(B <= 65535, "vote_tail: B too large");
-  const size_t smem = (size_t)D * (VT_SEEDS + 1) * sizeof(float);
-  vote_tail_kernel<<<dim3(ceil_div(S, VT_SEEDS), B), 256, smem, (cudaStream_t)stream_>>>(
-      net, bias, seed_xyz, (const __half *)seed_pm_f16, S, D, vote_xyz, vote_feat_cm,
-      (__half *)vote_pm_f16);
-  SPC_LAUNCH_CHECK("vote_tail_kernel");
-  return SPC_OK;
-}
-
-extern "C" int spc_pm_to_cm(const void *pm_f16, int B, int n, int C, float *cm, void *stream_) {
-  SPC_CHECK_ARG(B >= 0 && n >= 0 && C >= 0, "pm_to_cm: bad sizes");
-  if (B == 0 || n == 0 || C == 0) return SPC_OK;
-  SPC_CHECK_ARG(pm_f16 && cm, "pm_to_cm: null pointer");
-  SPC_CHECK_ARG(B <= 65535 && ceil_div(C, 32) <= 65535, "pm_to_cm: B or C too large");
-  pm_to_cm_kernel<<<dim3(ceil_div(n, 32), ceil_div(C, 32), B), 256, 0, (cudaStream_t)stream_>>>(
-      (const __half *)pm_f16, n, C, cm);
-  SPC_LAUNCH_CHECK("pm_to_cm_kernel");
   return SPC_OK;
 }

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 from . import _ext
 from .pointnet2_modules import (FoldedChain, PointnetFPModule, PointnetSAModuleVotes, _cache_of, attach_pm, fast_eval_ok,
-                                get_pm)
+                                get_pm, get_pm_pair)
 
 # ScanNet per-class mean box sizes (18 x 3, float64, every digit: the decoded corners must equal the reference's
 # bit for bit): dataset metadata shipped by the reference as
@@ -126,21 +126,23 @@ class VotingModule(nn.Module):
         return vote_xyz, vote_features.transpose(2, 1).contiguous()
 
     def forward_normalized_fast(self, seed_xyz, seed_features):
-        """Eval fast path returning (vote_xyz, L2-normalised vote_features) or None: three point-major
-        fp16 GEMMs (BN folded, bias+ReLU in the GEMM epilogue, the last one with fp32 output) and ONE
-        tail kernel for offsets, residual, normalisation and both output layouts."""
-        pm = get_pm(seed_features)
-        if (self.training or self.vote_factor != 1 or pm is None or self.out_dim > 256
+        """Eval fast path returning (vote_xyz, L2-normalised vote_features) or None: three tcgen05 launches
+        (spc_pm_linear: BN folded, fp16-pair operands, fp32-grade); offsets, residual, normalisation and both output
+        layouts are the epilogue of the last one."""
+        pm, pm_lo = get_pm_pair(seed_features)
+        if (self.training or self.vote_factor != 1 or pm is None or self.out_dim > 256 or self.in_dim % 64
                 or not fast_eval_ok(seed_xyz, seed_features)):
             return None
-        chain = _cache_of(self, FoldedChain).get([(self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, None)])
+        chain = _cache_of(self, FoldedChain).get([(self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, None)],
+                                                 last_rows_rotate=3)          # features first, xyz offsets last
         B, S, D = pm.shape
-        h = pm.reshape(B * S, D)
-        h = torch._addmm_activation(chain[0][1], h, chain[0][0])
-        h = torch._addmm_activation(chain[1][1], h, chain[1][0])
-        net = torch.mm(h, chain[2][0], out_dtype=torch.float32)          # (B*S, 3+D), bias added in the tail
-        vote_xyz, vote_features, vote_pm = _ext.vote_tail(net, chain[2][2], seed_xyz.contiguous(), pm)
-        return vote_xyz, attach_pm(vote_features, vote_pm)
+        h = pm.reshape(B * S, D) if pm_lo is None else (pm.reshape(B * S, D), pm_lo.reshape(B * S, D))
+        h = _ext.pm_linear(h, chain[0][0], chain[0][1], _ext.PM_HIDDEN, S)
+        h = _ext.pm_linear(h, chain[1][0], chain[1][1], _ext.PM_HIDDEN, S)
+        vote_xyz, vote_features, (hi, lo) = _ext.pm_linear(h, chain[2][0], chain[2][1], _ext.PM_VOTE, S,
+                                                           seed_cm=seed_features.contiguous(),
+                                                           seed_xyz=seed_xyz.contiguous())
+        return vote_xyz, attach_pm(vote_features, hi.view(B, S, D), lo.view(B, S, D))
 
 
 class ProposalModule(nn.Module):
@@ -177,13 +179,13 @@ class ProposalModule(nn.Module):
         data_dict["aggregated_vote_features"] = features.permute(0, 2, 1).contiguous()
         data_dict["aggregated_vote_inds"] = fps_inds
         pm = get_pm(features)
-        if not self.training and pm is not None and fast_eval_ok(features):
+        if not self.training and pm is not None and pm.shape[2] % 64 == 0 and fast_eval_ok(features):
             chain = _cache_of(self, FoldedChain).get(
                 [(self.proposal[0], self.proposal[1]), (self.proposal[3], self.proposal[4]), (self.proposal[6], None)])
             B, K, D = pm.shape
-            h = torch._addmm_activation(chain[0][1], pm.reshape(B * K, D), chain[0][0])
-            h = torch._addmm_activation(chain[1][1], h, chain[1][0])
-            t = torch.addmm(chain[2][2], h.float(), chain[2][0].float()).view(B, K, -1)   # fp32 head output
+            h = _ext.pm_linear(pm.reshape(B * K, D), chain[0][0], chain[0][1], _ext.PM_HIDDEN, K)
+            h = _ext.pm_linear(h, chain[1][0], chain[1][1], _ext.PM_HIDDEN, K)
+            t = _ext.pm_linear(h, chain[2][0], chain[2][1], _ext.PM_OUT_PM32, K).view(B, K, -1)   # fp32 head output
             return self.decode_scores(None, data_dict, net_transposed=t)
         net = self.proposal(features)
         return self.decode_scores(net, data_dict)

@@ -53,24 +53,30 @@ def _sample_centres(xyz, npoint, inds=None):
 INLINE_MAX_FEATURES = 16   # raw feature channels the fused kernel evaluates in-line (layer 0)
 
 
-def attach_pm(t, pm):
-    """Tag fp32 tensor `t` (B,C,n) with its point-major 16-bit copy `pm` (B,n,C) for the next fast-path stage.
+def attach_pm(t, pm, pm_lo=None):
+    """Tag fp32 tensor `t` (B,C,n) with its point-major 16-bit copy `pm` (B,n,C) for the next fast-path stage
+    (optionally as a hi + lo fp16 pair, t ~= pm + pm_lo to fp32 accuracy).
     The tag records t's version counter and storage pointer: any in-place edit of `t` between layers
     (`features.mul_(mask)`, in-place dropout, `copy_`) invalidates the copy instead of being silently ignored."""
-    t._spc_pm = (pm, t._version, t.data_ptr())
+    t._spc_pm = (pm, t._version, t.data_ptr(), pm_lo)
     return t
+
+
+def get_pm_pair(t):
+    """(hi, lo-or-None) attached to `t` by attach_pm, or (None, None) when absent, stale or mis-shaped."""
+    tag = getattr(t, "_spc_pm", None)
+    if tag is None:
+        return None, None
+    pm, version, ptr, pm_lo = tag
+    if version != t._version or ptr != t.data_ptr() or pm.device != t.device or t.dim() != 3 \
+            or pm.shape != (t.shape[0], t.shape[2], t.shape[1]):
+        return None, None
+    return pm, pm_lo
 
 
 def get_pm(t):
     """The point-major copy attached to `t` by attach_pm, or None when absent, stale or mis-shaped."""
-    tag = getattr(t, "_spc_pm", None)
-    if tag is None:
-        return None
-    pm, version, ptr = tag
-    if version != t._version or ptr != t.data_ptr() or pm.device != t.device or t.dim() != 3 \
-            or pm.shape != (t.shape[0], t.shape[2], t.shape[1]):
-        return None
-    return pm
+    return get_pm_pair(t)[0]
 
 
 # BN-folded weight caches live OUTSIDE the modules' __dict__: nn.DataParallel's replicate() shallow-copies that
@@ -145,11 +151,11 @@ class _FoldedMLP:
         return self._host0
 
     def w0f(self, W0):
-        """(C1, Cf) fp16: feature columns of the folded conv0 for the projection GEMM (F.linear: the "TN" layout,
-        for which cuBLAS picks its sm_100 kernels; the transposed "NN" form got a legacy sm_75 tensor-op kernel
-        for the 16384 x 128 x 128 case, 24 us instead of ~7)."""
+        """((C1, Cf) fp16 hi, lo): feature columns of the folded conv0 for the projection layer (spc_pm_linear),
+        plus a zero bias."""
         if self._w0f_t is None:
-            self._w0f_t = W0[:, 3:].contiguous().to(_ext.HALF)
+            self._w0f_t = (_ext.split_half(W0[:, 3:].contiguous()),
+                           torch.zeros(W0.shape[0], dtype=torch.float32, device=W0.device))
         return self._w0f_t
 
     def w0x(self, W0):
@@ -188,15 +194,16 @@ def fold_conv_bn_pair(conv, bn):
 
 
 class FoldedChain:
-    """Cache of a conv(+BN)(+ReLU) chain as point-major GEMM operands: [(W^T (Cin,Cout) fp16, b fp16)],
+    """Cache of a conv(+BN)(+ReLU) chain as operands of spc_pm_linear: [((W_hi, W_lo) (Cout,Cin) fp16 pair, b f32)],
     refreshed when a parameter / running statistic changes (tensor versions)."""
 
     def __init__(self):
         self.key = None
         self.layers = None
 
-    def get(self, pairs):
-        """pairs: list of (conv, bn_or_None)."""
+    def get(self, pairs, last_rows_rotate=0):
+        """pairs: list of (conv, bn_or_None).  last_rows_rotate = r moves the first r output channels of the LAST
+        layer behind the others (the voting tail wants conv3's feature rows first, its xyz-offset rows last)."""
         tensors = []
         for conv, bn in pairs:
             tensors += list(conv.parameters()) + (list(bn.parameters()) + list(bn.buffers()) if bn is not None else [])
@@ -206,8 +213,10 @@ class FoldedChain:
             self.layers = []
             for conv, bn in pairs:
                 W, b = fold_conv_bn_pair(conv, bn)
-                self.layers.append((W.t().contiguous().to(_ext.HALF), b.to(_ext.HALF).contiguous(),
-                                    b.contiguous()))
+                if last_rows_rotate and conv is pairs[-1][0]:
+                    r = last_rows_rotate
+                    W, b = torch.cat([W[r:], W[:r]], 0), torch.cat([b[r:], b[:r]], 0)
+                self.layers.append((_ext.split_half(W.contiguous()), b.contiguous()))
         return self.layers
 
 
@@ -355,13 +364,19 @@ class PointnetSAModuleVotes(nn.Module):
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, W0, b0, W1, b1, W2, b2, feat=feat,
                                                     radius=radius, want_point_major=True, W0_host=W0h, b0_host=b0h)
             else:
-                # conv0 hoisted out of the grouping: ONE fp16 GEMM over the n points gives the
+                # conv0 hoisted out of the grouping: ONE tcgen05 layer over the n points gives the
                 # per-point feature projection; the xyz columns stay in fp32 inside the kernel
-                pm = get_pm(features)                          # point-major fp16 copy from the producer
+                pm, pm_lo = get_pm_pair(features)              # point-major fp16 copy from the producer
                 if pm is None:
-                    pm = features.transpose(1, 2).to(_ext.HALF)
+                    pm, pm_lo = _ext.split_half(features.transpose(1, 2))
                 Bn = pm.shape[0] * pm.shape[1]
-                G = torch.nn.functional.linear(pm.reshape(Bn, Cf), cache.w0f(W0)).view(pm.shape[0], pm.shape[1], -1)
+                Wp, zero = cache.w0f(W0)
+                if Cf % 64 == 0 and W0.shape[0] % 32 == 0:
+                    X = pm.reshape(Bn, Cf) if pm_lo is None else (pm.reshape(Bn, Cf), pm_lo.reshape(Bn, Cf))
+                    G, _ = _ext.pm_linear(X, Wp, zero, _ext.PM_LINEAR, pm.shape[1], want_lo=False)
+                else:        # channel counts the tcgen05 layer does not take (e.g. 132 raw input channels)
+                    G = torch.nn.functional.linear(pm.reshape(Bn, Cf), Wp[0])
+                G = G.view(pm.shape[0], pm.shape[1], -1)
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, cache.w0x(W0), b0, W1, b1, W2, b2,
                                                     G=G, radius=radius, want_point_major=True)
             return attach_pm(out, out_pm)       # lets the next layer skip its transpose + cast
@@ -417,9 +432,9 @@ class PointnetFPModule(nn.Module):
 
     # -- fp16 point-major eval path -------------------------------------------------------------------
     def _forward_fast(self, unknown, known, unknow_feats, known_feats):
-        """three_nn+weights (1 kernel) -> interpolate+concat (1 kernel, point-major fp16) -> one
-        cuBLASLt GEMM with fused bias+ReLU per MLP layer -> channel-major fp32 copy for the API.
-        Needs the point-major fp16 copies that the fused SA / FP kernels attach to their outputs."""
+        """three_nn+weights (1 kernel) -> interpolate+concat (1 kernel, point-major fp16) -> one tcgen05 launch per
+        MLP layer (spc_pm_linear: fp16-pair operands, fp32-grade; the last one also writes the API's channel-major
+        fp32 tensor).  Needs the point-major copies that the fused SA / FP kernels attach to their outputs."""
         if self.training or known is None or not fast_eval_ok(unknown, known, unknow_feats, known_feats):
             return None
         kpm, spm = get_pm(known_feats), get_pm(unknow_feats)
@@ -432,16 +447,18 @@ class PointnetFPModule(nn.Module):
                 return None
             pairs.append((conv, norm.bn if norm is not None else None))
         chain = _cache_of(self, FoldedChain).get(pairs)
-        if chain[0][0].shape[0] != kpm.shape[2] + spm.shape[2]:
+        if chain[0][0][0].shape[1] != kpm.shape[2] + spm.shape[2] or any(W[0].shape[1] % 64 or W[0].shape[0] % 32
+                                                                         for W, _ in chain):
             return None
         idx, weight = _ext.three_nn_weights(unknown.contiguous(), known.contiguous())
         X = _ext.interp_cat_pm(kpm, idx, weight, spm)
         B, n = X.shape[0], X.shape[1]
         h = X.view(B * n, -1)
-        for Wt, b16, _ in chain:
-            h = torch._addmm_activation(b16, h, Wt)          # relu(h @ Wt + b), bias+ReLU in the GEMM epilogue
-        out_pm = h.view(B, n, -1)
-        return attach_pm(_ext.pm_to_cm(out_pm), out_pm)
+        for W, b in chain[:-1]:
+            h = _ext.pm_linear(h, W, b, _ext.PM_HIDDEN, n)      # relu(h @ W^T + b), fp16 pair out
+        W, b = chain[-1]
+        out, (hi, lo) = _ext.pm_linear(h, W, b, _ext.PM_OUT_CM, n)     # fp32 channel-major for the API + pm pair
+        return attach_pm(out, hi.view(B, n, -1), lo.view(B, n, -1))
 
 
 class PointnetLFPModuleMSG(nn.Module):

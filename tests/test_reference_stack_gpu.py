@@ -28,9 +28,11 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-2
-# FP1/FP2/voting stack six more 16-bit GEMM layers (K = 512 / 256) on top of the four SA MLPs; their element-wise
-# error relative to |ref| + rms is measured at 0.8-1.3e-2 end to end (profiles/r2_reference_stack_parity.txt)
-TOL_E2E_HEADS = 2e-2
+# The voting module (three more layers, then an L2 normalisation) amplifies the 3-5e-3 the four fused fp16 SA MLPs
+# leave on its input: vote features / offsets are measured at 0.9-1.3e-2 end to end
+# (profiles/r2_reference_stack_parity.txt); the FP / voting / proposal layers themselves are fp32-grade
+# (tests/test_pm_linear_gpu.py) and add nothing measurable.
+TOL_E2E_VOTES = 1.5e-2
 
 
 def _stack_or_skip():
@@ -76,8 +78,10 @@ def test_fast_mode_features_elementwise(report, tag):
     for i in (1, 2, 3, 4):
         assert r["sa%d_features:nerr" % i] <= TOL, (i, r["sa%d_features:nerr" % i])
         assert r["stage|sa%d_features:nerr" % i] <= TOL, (i, r["stage|sa%d_features:nerr" % i])
-    for k in ("fp2_features", "seed_features", "vote_features", "vote_offset"):
-        assert r[k + ":nerr"] <= TOL_E2E_HEADS, (k, r[k + ":nerr"])
+    for k in ("fp2_features", "seed_features"):
+        assert r[k + ":nerr"] <= TOL, (k, r[k + ":nerr"])
+    for k in ("vote_features", "vote_offset"):
+        assert r[k + ":nerr"] <= TOL_E2E_VOTES, (k, r[k + ":nerr"])
     assert r["vote_xyz:nerr"] <= TOL
     import refparity
     for k in refparity.PROPOSAL_KEYS:
