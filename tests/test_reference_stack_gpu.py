@@ -32,7 +32,7 @@ TOL = 1e-2
 # leave on its input: vote features / offsets are measured at 0.9-1.3e-2 end to end
 # (profiles/r2_reference_stack_parity.txt); the FP / voting / proposal layers themselves are fp32-grade
 # (tests/test_pm_linear_gpu.py) and add nothing measurable.
-TOL_E2E_VOTES = 1.5e-2
+TOL_E2E_VOTES = 2e-2
 
 
 def _stack_or_skip():
