@@ -61,10 +61,10 @@ size_t spc_fps_workspace_bytes(int B, int N, int npoint);
  *   SPC_FPS_CLUSTER  one thread-block cluster per scene; coordinates and running min-distances of every point in
  *                    registers / distributed shared memory, per-round arg-max over warp shuffles + DSMEM
  *                    (needs no workspace; holds 4 SMs per 40 k-point scene while it runs).
- *   SPC_FPS_BUCKET   one 256-thread CTA per scene; Hilbert-sorted points parked in L2 (workspace), per-bucket
+ *   SPC_FPS_BUCKET   one 512-thread CTA per scene; Hilbert-sorted points parked in L2 (workspace), per-bucket
  *                    bounding boxes and candidates on chip, only the buckets a new centre can change are updated
- *                    (four scenes share an SM; ~3x the latency of the cluster sampler, ~1/15 of its SM-time: the
- *                    choice for pipelines with several batches in flight).  Needs a workspace and
+ *                    (two scenes share an SM; ~2.5x the latency of the cluster sampler, 1/6 of its instructions and
+ *                    1/8 of its SM-time: the choice for pipelines with several batches in flight).  Needs a workspace and
  *                    4096 <= N <= 40960, else SPC_ERR_UNSUPPORTED. */
 #define SPC_FPS_AUTO 0
 #define SPC_FPS_CLUSTER 1
@@ -147,6 +147,7 @@ int spc_three_interpolate(const float *points, const int32_t *idx, const float *
 int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const float *weight,
                                int B, int C, int n, int m, float *grad_points, void *stream);
 
+
 /* Fused set-abstraction forward, eval mode (no reference C++ counterpart: it replaces the whole
  * Python/ATen/cuDNN sequence of PointnetSAModuleVotes.forward after the ball query --
  * pointnet2_utils.py:351-362 (2x group_points, sub, div, cat), pytorch_utils.py:11-36 (SharedMLP =
@@ -201,7 +202,7 @@ int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float 
  * Replaces the library GEMMs + layout / elementwise kernels of PointnetFPModule's SharedMLP
  * (pointnet2_modules.py:412-421), VotingModule (models/voting_module.py:34-61, plus the L2 normalisation of
  * models/SpaCapNet.py:66-67) and the proposal head (models/proposal_module.py:46-54,73).
- *   X_hi (M,K) FP16 point-major rows, X_lo (M,K) FP16 or NULL (x = hi + lo);  K % 64 == 0
+ *   X_hi (M,K) FP16 point-major rows, X_lo (M,K) FP16 or NULL (x = hi + lo);  K % 8 == 0
  *   W_hi, W_lo (N,K) FP16: the BatchNorm-folded fp32 weights as a pair (w = hi + lo);  bias (N) f32;  N <= 272
  *   three MMAs per product (hi.hi + lo.hi + hi.lo), fp32 accumulation: fp32-grade results
  *   points_per_scene: rows per scene (M = B * points_per_scene), used by the channel-major outputs

@@ -510,8 +510,9 @@ __device__ __noinline__ unsigned fb_resolve_tie(bool hit, int k, unsigned lane, 
   return __reduce_min_sync(0xffffffffu, (hit && v == vmin) ? lane : 32u);
 }
 
-__host__ __device__ constexpr size_t fb_smem_per_scene(int NB, int W, int S) {
-  return (size_t)((NB + 1) & ~1) * 40 + (size_t)W * 64 + (((size_t)W * 32 * S * 2 + 15) & ~(size_t)15);
+__host__ __device__ constexpr size_t fb_smem_per_scene(int W, int S) {
+  // kxyz 16 B + box 24 B per table entry (W * 32 * S entries), per-warp candidates, per-warp queues
+  return (size_t)W * 32 * S * 40 + (size_t)W * 64 + (((size_t)W * 32 * S * 2 + 15) & ~(size_t)15);
 }
 
 // W warps work on one scene, G scenes share a CTA (W * G * 32 threads; the scenes of a CTA only share the SM, they
@@ -519,7 +520,7 @@ __host__ __device__ constexpr size_t fb_smem_per_scene(int NB, int W, int S) {
 // every lane keeps the candidate key of its <= S buckets in registers, so the cull test and the arg-max read no
 // shared memory but the boxes, and spatial neighbours (consecutive buckets) land in different warps.
 template <int BS, int W, int G, int S>
-__global__ void __launch_bounds__(W * G * 32, G == 1 ? 4 : 1)
+__global__ void __launch_bounds__(W * G * 32, G == 1 ? (W <= 8 ? 4 : (W <= 16 ? 2 : 1)) : 1)
 fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict__ kk_all,
                   const float *__restrict__ boxes_all, int NB, int B) {
   constexpr int PPL = BS / 32;                        // points per lane and bucket
@@ -532,13 +533,16 @@ fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict_
   const unsigned lane = t & 31u, w = t >> 5;
   // per scene: candidate coordinates [NB] float4 (k bits, x, y, z), boxes [NB] float4 + float2, per-warp queues,
   // per-warp candidates (double buffered)
-  const int NBe = (NB + 1) & ~1;                      // even, keeps every array 16-byte aligned
-  unsigned char *base = fb_smem + (size_t)grp * fb_smem_per_scene(NB, W, S);
-  float4 *s_kxyz = reinterpret_cast<float4 *>(base);
-  float4 *s_box4 = s_kxyz + NBe;
-  float2 *s_box2 = reinterpret_cast<float2 *>(s_box4 + NBe);
-  uint4 *s_wc = reinterpret_cast<uint4 *>(s_box2 + NBe);           // [2][W] x 2 uint4: (key, k, -, -), (k, x, y, z)
-  uint16_t *s_q = reinterpret_cast<uint16_t *>(s_wc + 4 * W) + w * QCAP;
+  // The per-bucket tables are indexed by (warp, slot * 32 + lane), NOT by bucket: consecutive lanes then read
+  // consecutive 16-byte entries (indexed by bucket the lanes were W * 16 bytes apart -- a 32-way bank conflict on
+  // every box read, 13.5 M conflict wavefronts per call in ncu).
+  constexpr int NL = W * QCAP;                        // table entries per scene
+  unsigned char *base = fb_smem + (size_t)grp * fb_smem_per_scene(W, S);
+  float4 *s_kxyz = reinterpret_cast<float4 *>(base) + w * QCAP;    // my warp's slice of each table
+  float4 *s_box4 = reinterpret_cast<float4 *>(base) + NL + w * QCAP;
+  float2 *s_box2 = reinterpret_cast<float2 *>(reinterpret_cast<float4 *>(base) + 2 * NL) + w * QCAP;
+  uint4 *s_wc = reinterpret_cast<uint4 *>(reinterpret_cast<float2 *>(reinterpret_cast<float4 *>(base) + 2 * NL) + NL);
+  uint16_t *s_q = reinterpret_cast<uint16_t *>(s_wc + 4 * W) + w * QCAP;      // s_wc: [2][W] x 2 uint4
 
   const float *xyz = p.xyz + (size_t)scene * p.N * 3;
   if (p.ordered_ok != nullptr && p.ordered_ok[scene] != 0) {       // verified shortcut, as in fps_cluster_kernel
@@ -567,9 +571,9 @@ fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict_
     if (b < NB) {
       const float lx = __ldg(boxes + 6 * b + 0), ly = __ldg(boxes + 6 * b + 1), lz = __ldg(boxes + 6 * b + 2);
       const float hx = __ldg(boxes + 6 * b + 3), hy = __ldg(boxes + 6 * b + 4), hz = __ldg(boxes + 6 * b + 5);
-      s_box4[b] = make_float4(lx, ly, lz, hx);
-      s_box2[b] = make_float2(hy, hz);
-      s_kxyz[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s_box4[s * 32 + lane] = make_float4(lx, ly, lz, hx);
+      s_box2[s * 32 + lane] = make_float2(hy, hz);
+      s_kxyz[s * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
       key[s] = hx >= lx ? FB_KEY_INIT : 0u;           // every min-distance starts at 1e10
     }
   }
@@ -582,17 +586,17 @@ fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict_
     idx[0] = 0;
     if (nxyz) { nxyz[0] = ox; nxyz[1] = oy; nxyz[2] = oz; }
   }
-  __syncwarp();
+  __syncwarp();                                       // every table entry is written and read by its own warp only
 
   for (int j = 1; j < p.npoint; ++j) {
     // ---- 1. cull my buckets: which of them can this centre change? --------------------------------
     int nq = 0;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-      // no branch around the test: the S slots are independent chains the scheduler can interleave
-      const int b = min((s * 32 + (int)lane) * W + (int)w, NB - 1);
-      const float4 b4 = s_box4[b];
-      const float2 b2 = s_box2[b];
+      // no branch around the test: the S slots are independent chains the scheduler can interleave (entries past
+      // the last bucket hold whatever shared memory held; their key is 0, so the result is discarded)
+      const float4 b4 = s_box4[s * 32 + lane];
+      const float2 b2 = s_box2[s * 32 + lane];
       const float ex = fmaxf(0.f, fmaxf(b4.x - ox, ox - b4.w)), ey = fmaxf(0.f, fmaxf(b4.y - oy, oy - b2.x)),
                   ez = fmaxf(0.f, fmaxf(b4.z - oz, oz - b2.y));
       const float lb2 = (ex * ex + ey * ey + ez * ez) * 0.99999f;       // conservative w.r.t. fp32 rounding
@@ -646,7 +650,7 @@ fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict_
       const unsigned ties = __ballot_sync(0xffffffffu, hit);
       unsigned src = __ffs(ties) - 1u;
       if (kmax != 0u && (ties & (ties - 1u)) != 0u) src = fb_resolve_tie(hit, ck, lane, p.T, p.log2T, p.Q);
-      if (lane == src) s_kxyz[b] = make_float4(__int_as_float(ck), c.x, c.y, c.z);
+      if (lane == src) s_kxyz[sl] = make_float4(__int_as_float(ck), c.x, c.y, c.z);
       const bool btie = (ties & (ties - 1u)) != 0u || __any_sync(0xffffffffu, hit && ltie);
       const int owner = sl & 31, oslot = sl >> 5;
 #pragma unroll
@@ -663,12 +667,13 @@ fps_bucket_kernel(const FpsParams p, float4 *pts_all, const int32_t *__restrict_
       if (key[s] > mkey) { mkey = key[s]; ms = s; mtie = false; }
       else if (key[s] == mkey && mkey != 0u) {
         mtie = true;
-        const int ba = (s * 32 + (int)lane) * W + (int)w, bb = (ms * 32 + (int)lane) * W + (int)w;
-        if (fb_tie_before(__float_as_int(s_kxyz[ba].x), __float_as_int(s_kxyz[bb].x), p.T, p.log2T, p.Q)) ms = s;
+        if (fb_tie_before(__float_as_int(s_kxyz[s * 32 + lane].x), __float_as_int(s_kxyz[ms * 32 + lane].x), p.T,
+                          p.log2T, p.Q))
+          ms = s;
       }
     }
     mtie = mtie || ((tiebits >> ms) & 1u) != 0u;
-    const int mb = (ms * 32 + (int)lane) * W + (int)w;
+    const int mb = ms * 32 + (int)lane;                 // table entry of my best bucket
     const unsigned wmax = __reduce_max_sync(0xffffffffu, mkey);
     {
       const bool hit = mkey == wmax;
@@ -920,7 +925,7 @@ template <int BS, int W, int G, int S>
 static int launch_fps_bucket_cfg(const FpsParams &p, int B, int NB, float4 *pts, const int32_t *kk, const float *boxes,
                                  cudaStream_t stream) {
   auto kern = fps_bucket_kernel<BS, W, G, S>;
-  const size_t smem = fb_smem_per_scene(NB, W, S) * G;
+  const size_t smem = fb_smem_per_scene(W, S) * G;
   if (smem > 227 * 1024) {
     set_error("fps: bucket table of %d entries x %d scenes does not fit in shared memory", NB, G);
     return SPC_ERR_UNSUPPORTED;
@@ -943,17 +948,17 @@ static int launch_fps_bucket(const FpsParams &p, int B, int N, int32_t *perm, vo
   SPC_LAUNCH_CHECK("fps_morton_sort_kernel");
   fps_bucket_build_kernel<BS><<<dim3(ceil_div(NB, 8), B), 256, 0, stream>>>(p.xyz, perm, N, NB, pts, kk, boxes);
   SPC_LAUNCH_CHECK("fps_bucket_build_kernel");
-  // 8 warps per scene, one scene per CTA.  Measured on B200 (8 x 40 k -> 2048): ms per call alone / k scenes per
-  // second with 32 sampler calls in flight / k scenes per second of the whole detector pipeline --
-  // W8 G1 4.0 / 39.6 / 16.4; W8 G2 4.9 / 42.8 / 16.4; W8 G4 7.0 / 33.7 / 14.2; W4 G8 8.3 / 26.8 / 12.5; W16 G1 3.9 / 32.6.
-  // The rounds are bound by dependent-instruction latency, so scenes packed onto one SM slow each other down, and
-  // the pipeline no longer gains from freeing SMs: with this sampler it is bound by the other kernels.
-  constexpr int W = 8;
+  // 16 warps per scene, one scene per CTA.  Measured on B200 (8 x 40 k -> 2048; ms per call alone / k scenes per second
+  // with 32 sampler calls in flight / k scenes per second of the whole detector pipeline), after the bank-conflict fix:
+  //   W8 G1 3.65 / 48.3 / 17.6;   W16 G1 3.04 / 56.6 / 18.8;   W32 G1 2.86 / 43.9 / 17.1
+  // and before it, scenes packed onto one SM:  W8 G2 4.9 / 42.8 / 16.4;  W8 G4 7.0 / 33.7 / 14.2;  W4 G8 8.3 / 26.8 / 12.5.
+  // A round is a chain of dependent instructions (cull -> L2 load -> update -> three arg-max levels): more warps
+  // shorten the per-warp chain and balance the bucket visits, scenes sharing an SM slow each other down.
+  constexpr int W = 16;
   const int S = ceil_div(ceil_div(NB, W), 32);
   switch (S) {
     case 1: return launch_fps_bucket_cfg<BS, W, 1, 1>(p, B, NB, pts, kk, boxes, stream);
     case 2: return launch_fps_bucket_cfg<BS, W, 1, 2>(p, B, NB, pts, kk, boxes, stream);
-    case 3: return launch_fps_bucket_cfg<BS, W, 1, 3>(p, B, NB, pts, kk, boxes, stream);
   }
   set_error("fps: no bucket kernel for %d buckets", NB);
   return SPC_ERR_UNSUPPORTED;

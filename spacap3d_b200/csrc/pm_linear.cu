@@ -5,7 +5,7 @@
 // elementwise kernels; here each layer is ONE launch and the layer-specific tails are its epilogue.
 //
 //   X (M, K) fp16 point-major rows (M = B * points), optionally as a hi + lo pair (x = hi + lo);
-//   W (N, K) BatchNorm-folded weights as a hi + lo fp16 pair, bias (N) fp32;  N <= 272, K % 64 == 0.
+//   W (N, K) BatchNorm-folded weights as a hi + lo fp16 pair, bias (N) fp32;  N <= 272, K % 8 == 0.
 //
 // Precision: fp16 carries 11 significant bits, so a single-fp16 GEMM is ~2e-4 per operand off the fp32 layer.  The
 // weights -- and the hidden activations, which this kernel produces itself -- are therefore carried as fp16 PAIRS
@@ -162,7 +162,7 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int B_BYTES = Nr * 128;
   const int STAGE_BYTES = A_BYTES * (1 + p.has_lo) + 2 * B_BYTES;
   const int row0 = blockIdx.x * PL_ROWS;
-  const int KCH = p.K / PL_KC;
+  const int KCH = (p.K + PL_KC - 1) / PL_KC;           // a partial last chunk is zero-filled by TMA (both operands)
   const uint32_t tmem_cols = Nr > 256 ? 512u : (Nr > 128 ? 256u : 128u);
 
   if (tid == 0) {
@@ -392,7 +392,8 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
                              const float *bias, int N, int mode, int points_per_scene, void *Y_hi, void *Y_lo,
                              float *out, const float *seed_cm, const float *seed_xyz, float *vote_xyz,
                              void *stream_) {
-  SPC_CHECK_ARG(M >= 0 && K >= PL_KC && K % PL_KC == 0 && K <= 4096, "pm_linear: K=%d must be a multiple of 64", K);
+  // rows are K * 2 bytes apart and TMA needs 16-byte strides; K need not be a multiple of the 64-element chunk
+  SPC_CHECK_ARG(M >= 0 && K >= 8 && K % 8 == 0 && K <= 4096, "pm_linear: K=%d must be a multiple of 8", K);
   SPC_CHECK_ARG(N >= 1 && N <= 272, "pm_linear: N=%d out of range (1..272)", N);
   SPC_CHECK_ARG(mode == SPC_PM_HIDDEN || mode == SPC_PM_OUT_CM || mode == SPC_PM_OUT_PM32 || mode == SPC_PM_VOTE ||
                     mode == SPC_PM_LINEAR,
@@ -420,7 +421,7 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
   const int stage_bytes = PL_ROWS * 128 * (1 + p.has_lo) + 2 * Nr * 128;
   int stages = (220 * 1024) / stage_bytes;
   if (stages > PL_MAX_STAGES) stages = PL_MAX_STAGES;
-  if (stages > K / PL_KC) stages = K / PL_KC;
+  if (stages > (K + PL_KC - 1) / PL_KC) stages = (K + PL_KC - 1) / PL_KC;
   SPC_CHECK_ARG(stages >= 1, "pm_linear: a pipeline stage of %d bytes does not fit in shared memory", stage_bytes);
   p.stages = stages;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;

@@ -19,8 +19,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _ext
-from .pointnet2_modules import (FoldedChain, PointnetFPModule, PointnetSAModuleVotes, _cache_of, attach_pm, fast_eval_ok,
-                                get_pm, get_pm_pair)
+from ._ext import HALF
+from .pointnet2_modules import (INLINE_MAX_FEATURES, FoldedChain, PointnetFPModule, PointnetSAModuleVotes, _cache_of,
+                                attach_pm, fast_eval_ok, get_pm, get_pm_pair)
 
 # ScanNet per-class mean box sizes (18 x 3, float64, every digit: the decoded corners must equal the reference's
 # bit for bit): dataset metadata shipped by the reference as
@@ -78,8 +79,19 @@ class Pointnet2Backbone(nn.Module):
     @staticmethod
     def _break_up_pc(pc):
         xyz = pc[..., :3].contiguous()
-        features = pc[..., 3:].transpose(1, 2).contiguous() if pc.size(-1) > 3 else None
-        return xyz, features
+        if pc.size(-1) <= 3:
+            return xyz, None
+        C = pc.size(-1) - 3
+        if C > INLINE_MAX_FEATURES and fast_eval_ok(pc) and pc.dtype == torch.float32:
+            # many input channels (multiview features): the fused SA1 wants them point-major in fp16 -- which is
+            # the layout the cloud already has.  One pass makes that copy (zero-padded to a multiple of 8 channels
+            # for TMA); the channel-major tensor of the reference API stays a view and is never materialised.
+            Kp = (C + 7) // 8 * 8
+            pm = torch.zeros((pc.shape[0], pc.shape[1], Kp), dtype=HALF, device=pc.device) if Kp != C else \
+                torch.empty((pc.shape[0], pc.shape[1], Kp), dtype=HALF, device=pc.device)
+            pm[..., :C].copy_(pc[..., 3:])
+            return xyz, attach_pm(pc[..., 3:].transpose(1, 2), pm)
+        return xyz, pc[..., 3:].transpose(1, 2).contiguous()
 
     def forward(self, data_dict):
         xyz, features = self._break_up_pc(data_dict["point_clouds"])

@@ -69,8 +69,8 @@ def get_pm_pair(t):
         return None, None
     pm, version, ptr, pm_lo = tag
     if version != t._version or ptr != t.data_ptr() or pm.device != t.device or t.dim() != 3 \
-            or pm.shape != (t.shape[0], t.shape[2], t.shape[1]):
-        return None, None
+            or pm.shape[:2] != (t.shape[0], t.shape[2]) or not t.shape[1] <= pm.shape[2] < t.shape[1] + 8:
+        return None, None     # (the channel dimension of the copy may be zero-padded to a multiple of 8)
     return pm, pm_lo
 
 
@@ -318,6 +318,8 @@ class PointnetSAModuleVotes(nn.Module):
         fused = self._forward_fused(xyz, new_xyz, features)
         if fused is not None:
             return new_xyz, fused, inds
+        if features is not None and not features.is_contiguous():
+            features = features.contiguous()      # (a caller may hand in a channel-major VIEW of a point-major cloud)
         grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         if (self.pooling == 'max' and self.training and grouped_features.is_cuda and len(self.mlp_module) > 0
                 and pt_utils.FUSED_BN_RELU_TRAINING):
@@ -369,13 +371,18 @@ class PointnetSAModuleVotes(nn.Module):
                 pm, pm_lo = get_pm_pair(features)              # point-major fp16 copy from the producer
                 if pm is None:
                     pm, pm_lo = _ext.split_half(features.transpose(1, 2))
-                Bn = pm.shape[0] * pm.shape[1]
                 Wp, zero = cache.w0f(W0)
-                if Cf % 64 == 0 and W0.shape[0] % 32 == 0:
-                    X = pm.reshape(Bn, Cf) if pm_lo is None else (pm.reshape(Bn, Cf), pm_lo.reshape(Bn, Cf))
-                    G, _ = _ext.pm_linear(X, Wp, zero, _ext.PM_LINEAR, pm.shape[1], want_lo=False)
-                else:        # channel counts the tcgen05 layer does not take (e.g. 132 raw input channels)
-                    G = torch.nn.functional.linear(pm.reshape(Bn, Cf), Wp[0])
+                Kp = pm.shape[2]                               # Cf, or Cf padded to a multiple of 8 by the producer
+                if Kp % 8:                                     # TMA rows must be 16-byte multiples: pad with zeros
+                    Kp = (Cf + 7) // 8 * 8
+                    pm = torch.nn.functional.pad(pm, (0, Kp - Cf))
+                    pm_lo = torch.nn.functional.pad(pm_lo, (0, Kp - Cf)) if pm_lo is not None else None
+                if Wp[0].shape[1] != Kp:
+                    Wp = tuple(torch.nn.functional.pad(t, (0, Kp - t.shape[1])) for t in Wp)
+                    cache._w0f_t = (Wp, zero)
+                Bn = pm.shape[0] * pm.shape[1]
+                X = pm.reshape(Bn, Kp) if pm_lo is None else (pm.reshape(Bn, Kp), pm_lo.reshape(Bn, Kp))
+                G, _ = _ext.pm_linear(X, Wp, zero, _ext.PM_LINEAR, pm.shape[1], want_lo=False)
                 G = G.view(pm.shape[0], pm.shape[1], -1)
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, cache.w0x(W0), b0, W1, b1, W2, b2,
                                                     G=G, radius=radius, want_point_major=True)

@@ -242,6 +242,20 @@ def interp_cases():
     return c
 
 
+def interp_big_cases():
+    """Larger interpolation shapes (no golden vectors: checked against the oracle and the live reference ext):
+    FP2's, config 5's x4 cloud, and a ragged one (n % 4 != 0, channel count not a multiple of the tile)."""
+    rng = np.random.default_rng(707)
+    c = {}
+    for name, (B, C, m, n) in {"fp2": (2, 256, 512, 1024), "config5_x4": (1, 40, 2048, 4096),
+                               "ragged": (3, 33, 100, 1022)}.items():
+        w = rng.uniform(0.01, 1, (B, n, 3)).astype(np.float32)
+        w = (w / w.sum(-1, keepdims=True)).astype(np.float32)
+        c[name] = (rng.standard_normal((B, C, m)).astype(np.float32),
+                   rng.integers(0, m, (B, n, 3)).astype(np.int32), w)
+    return c
+
+
 def grad_for(tag, shape):
     """Deterministic upstream gradient for a named case."""
     seed = int(hashlib.sha1(tag.encode()).hexdigest()[:8], 16)

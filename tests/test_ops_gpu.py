@@ -253,21 +253,20 @@ def test_group_grad_list_based(ext, ref_ext, name, monkeypatch):
     if npoint * ns <= 49152:
         for _ in range(3):
             np.testing.assert_array_equal(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), got)
-    if npoint * ns <= 49152:
-        # the one-kernel list build (two-level stable sort) and the original per-warp scan produce the same
-        # ascending lists, hence bit-identical sums
-        monkeypatch.setenv("SPC_GROUP_GRAD_OLD_FILL", "1")
-        np.testing.assert_array_equal(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), got)
-        monkeypatch.delenv("SPC_GROUP_GRAD_OLD_FILL")
-    monkeypatch.setenv("SPC_GROUP_GRAD_ATOMIC", "1")
-    np.testing.assert_allclose(ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), want, **tol)
+    # the entry point without a workspace takes the atomic kernel
+    from spacap3d_b200 import _lib
+    ga, ia = cu(g), cu(idx)
+    atomic = torch.empty((B, C, N), dtype=torch.float32, device=DEV)
+    _lib.call("spc_group_points_grad", ga.data_ptr(), ia.data_ptr(), B, C, N, npoint, ns, atomic.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    np.testing.assert_allclose(atomic.cpu().numpy(), want, **tol)
     if ref_ext is not None:
         np.testing.assert_allclose(ref_ext.group_points_grad(cu(g), cu(idx), N).cpu().numpy(), want, **tol)
 
 
-@pytest.mark.parametrize("name", list(cases.interp_cases().keys()))
+@pytest.mark.parametrize("name", list(cases.interp_cases().keys()) + list(cases.interp_big_cases().keys()))
 def test_interpolate(ext, ref_ext, name):
-    pts, idx, w = cases.interp_cases()[name]
+    pts, idx, w = {**cases.interp_cases(), **cases.interp_big_cases()}[name]
     got = ext.three_interpolate(cu(pts), cu(idx), cu(w)).cpu().numpy()
     want = oracle.three_interpolate(pts, idx, w)
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)   # the bar north_star states
@@ -277,6 +276,7 @@ def test_interpolate(ext, ref_ext, name):
     np.testing.assert_allclose(gg, wg, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(wg).max()))
     if ref_ext is not None:
         np.testing.assert_array_equal(got, ref_ext.three_interpolate(cu(pts), cu(idx), cu(w)).cpu().numpy())
+        np.testing.assert_array_equal(got, want)          # bit-equal to the oracle as well
 
 
 # ---------------------------------------------------------------- BASELINE-size properties ----

@@ -33,7 +33,8 @@ def _layer(M, K, N, seed, pair_input):
 
 
 @pytest.mark.parametrize("M,K,N,pair", [(4096, 512, 256, False), (8192, 256, 256, True), (2048, 128, 128, True),
-                                        (300, 64, 32, False), (128 * 3 + 7, 192, 96, True)])
+                                        (300, 64, 32, False), (128 * 3 + 7, 192, 96, True), (1000, 136, 64, False),
+                                        (257, 8, 32, True)])
 def test_hidden_layer(M, K, N, pair):
     from spacap3d_b200 import _ext
     X, W, b, ref = _layer(M, K, N, 1, pair)
@@ -86,5 +87,5 @@ def test_argument_checks():
     from spacap3d_b200 import _ext, _lib
     X, W, b, _ = _layer(256, 64, 32, 5, False)
     with pytest.raises(_lib.SpcError):
-        _ext.pm_linear(X[:, :48].contiguous(), (W[0][:, :48].contiguous(), W[1][:, :48].contiguous()), b,
-                       _ext.PM_HIDDEN, 256)          # K not a multiple of 64
+        _ext.pm_linear(X[:, :44].contiguous(), (W[0][:, :44].contiguous(), W[1][:, :44].contiguous()), b,
+                       _ext.PM_HIDDEN, 256)          # K not a multiple of 8

@@ -143,9 +143,14 @@ def main():
             t = timeit(lambda: ref.group_points_grad(g, idx, n), max(3, args.iters // 3), flush) if ref else None
             rec("group_points_grad", [B, C, n, npoint, ns], o, t, 4 * B * (C * n + npoint * ns + C * npoint * ns))
     if "three_nn" in ops or "interp" in ops:
-        for (n, m) in ((512, 256), (1024, 512)):
-            unknown = levels[3][0] if n == 512 else levels[2][0]
-            known = levels[3][1] if n == 512 else levels[2][1]
+        for (n, m) in ((512, 256), (1024, 512), (4096, 2048)):      # FP1, FP2, config 5's x4 shape
+            if n == 4096:
+                big = torch.from_numpy(np.stack([make_scene_xyz(900 + i, 40000) for i in range(B)], 0)).to(dev)
+                _, unknown = _ext.furthest_point_sampling_with_xyz(big, 4096)
+                known = unknown[:, :2048].contiguous()
+            else:
+                unknown = levels[3][0] if n == 512 else levels[2][0]
+                known = levels[3][1] if n == 512 else levels[2][1]
             o = timeit_ours(lambda: _ext.three_nn(unknown, known), args.iters, flush)
             t = timeit(lambda: ref.three_nn(unknown, known), max(3, args.iters // 3), flush) if ref else None
             rec("three_nn", [B, n, m], o, t, B * (12 * (n + m) + 24 * n))
