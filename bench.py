@@ -656,8 +656,11 @@ def run_train(args, rank, world, local, device, dist, barrier):
     """BASELINE config 5: forward + backward of the detector in training mode (autograd through the unfused
     sm_100a kernels and their backward passes + cuDNN convolutions + the fused BN/ReLU/max-pool training kernels)
     and ONE flat NCCL all-reduce of the gradients per step (the reference: nn.DataParallel, scripts/train.py:198-200).
-    The loss is a surrogate (mean square of the head outputs): lib/loss_helper.py is outside the path."""
+    The loss is a surrogate (mean square of the head outputs): lib/loss_helper.py is outside the path.
+    Forward + backward are captured once into a CUDA graph (the step has no host synchronisation: the box decode
+    stays on the device) and replayed on a static input; the all-reduce runs after the replay."""
     from tools import bench_train
+    from spacap3d_b200.dist import allreduce_gradients
     from spacap3d_b200.scenes import make_scene
     n, spg = args.points, scenes_per_gpu(world)
     scale = max(1, round(n / 40000))
@@ -667,15 +670,43 @@ def run_train(args, rank, world, local, device, dist, barrier):
                                        for i in range(spg)], 0)).pin_memory() for s in range(n_sets)]
     resident = [h.to(device) for h in host]
     flush = L2Flusher(device)
+    static_in = torch.empty_like(resident[0])
+    launches = [0]
+    from spacap3d_b200 import _lib
+    orig = _lib.call
+
+    def counting(name, *a):
+        launches[0] += 1
+        return orig(name, *a)
+
+    def fwd_bwd():
+        out = model({"point_clouds": static_in})
+        loss = bench_train.surrogate_loss(out)
+        loss.backward()
+        return loss.detach()
+
+    static_in.copy_(resident[0])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):                                     # lazy initialisations outside the capture
+            model.zero_grad(set_to_none=True)
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    model.zero_grad(set_to_none=True)
+    _lib.call = counting
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_loss = fwd_bwd()
+    _lib.call = orig
+    launches_per_step = launches[0]
     ar_events = []
 
     def step(pc, timed_ar=False):
-        model.zero_grad(set_to_none=True)
-        out = model({"point_clouds": pc})
-        loss = bench_train.surrogate_loss(out)
-        loss.backward()
+        static_in.copy_(pc, non_blocking=True)
+        graph.replay()
         if world > 1:
-            from spacap3d_b200.dist import allreduce_gradients
             if timed_ar:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -684,25 +715,14 @@ def run_train(args, rank, world, local, device, dist, barrier):
                 ar_events.append((e0, e1))
             else:
                 allreduce_gradients(model)
-        return loss
+        return static_loss
 
-    from spacap3d_b200 import _lib
-    launches = [0]
-    orig = _lib.call
-
-    def counting(name, *a):
-        launches[0] += 1
-        return orig(name, *a)
-    _lib.call = counting
     per_step, wall, clocks = timed_loop(lambda i: step(resident[i % n_sets], True), args.steps, args.warmup, flush,
                                         barrier, ClockSampler(local))
-    launches_per_step = launches[0] // (args.steps + args.warmup)
-    _lib.call = orig
     loss_holder = {}
 
     def step_e2e(i):
-        pc = host[i % n_sets].to(device, non_blocking=True)
-        loss_holder["l"] = float(step(pc))              # device -> host read of the loss
+        loss_holder["l"] = float(step(host[i % n_sets]))       # pinned host -> device ... device -> host read of the loss
 
     e2e_steps, _, _ = timed_loop(step_e2e, args.steps, args.warmup, flush, barrier)
     t = torch.tensor([sum(per_step), sum(e2e_steps)], device=device, dtype=torch.float64)
@@ -711,11 +731,27 @@ def run_train(args, rank, world, local, device, dist, barrier):
     dev_s, e2e_s = float(t[0]) / 1e3, float(t[1]) / 1e3
     ar_us = [a.elapsed_time(b) * 1e3 for a, b in ar_events[-args.steps:]] if ar_events else []
     n_params = sum(p.numel() for p in model.parameters())
+    # the collective alone: the same flat buffer, ranks aligned by a barrier, 20 back-to-back all-reduces
+    iso_us = None
+    if dist is not None:
+        flat = torch.zeros(n_params, device=device)
+        for _ in range(5):
+            dist.all_reduce(flat)
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            dist.all_reduce(flat)
+        e1.record()
+        torch.cuda.synchronize()
+        iso_us = e0.elapsed_time(e1) * 1e3 / 20
     if rank == 0:
         cfg = workload_config(world)
         cfg.update({"points": n, "sa_npoint_scale": scale, "mode": "training: forward + backward + gradient all-reduce",
                     "weights": "random init (seed 0), train mode",
-                    "l2": "256 MiB L2 flush between timed steps", "execution": "eager, 1 stream",
+                    "l2": "256 MiB L2 flush between timed steps",
+                    "execution": "forward + backward as one CUDA graph, 1 stream; all-reduce after the replay",
                     "parallelism": "scenes sharded by batch, %d rank(s), one flat NCCL all-reduce of %d gradients "
                                    "(%.1f MB) per step" % (world, n_params, n_params * 4 / 1e6)})
         line = {"metric": "detector training scenes/s (fwd+bwd+allreduce)", "value": round(spg * world * args.steps / dev_s, 3),
@@ -725,9 +761,12 @@ def run_train(args, rank, world, local, device, dist, barrier):
                 "e2e": {"value": round(spg * world * args.steps / e2e_s, 3), "unit": "scenes/s",
                         "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": 4,
                         "ms_per_step": round(e2e_s / args.steps * 1e3, 4)},
-                "allreduce": {"median_us": round(statistics.median(ar_us), 1) if ar_us else None,
-                              "bytes": n_params * 4, "note": "CUDA events around dist.allreduce_gradients on rank 0 "
-                              "(includes waiting for the slowest rank's backward)"},
+                "allreduce": {"in_step_median_us": round(statistics.median(ar_us), 1) if ar_us else None,
+                              "isolated_us": round(iso_us, 1) if iso_us is not None else None,
+                              "bytes": n_params * 4,
+                              "note": "in_step: CUDA events around dist.allreduce_gradients on rank 0 (flatten + NCCL "
+                                      "all-reduce + scatter back; includes waiting for the slowest rank's backward); "
+                                      "isolated: the NCCL all-reduce of the same flat buffer alone, ranks aligned"},
                 "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step),
                 "roofline": None, "cpu_baseline": None, "clocks": clocks, "wall_s_timed_region": round(wall, 4)}
         print(json.dumps(line))
