@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(BQG_BUILD_THREADS) bqg_build_kernel(const floa
 // one warp per centre
 __global__ void __launch_bounds__(BQG_THREADS) bqg_query_kernel(const float *__restrict__ new_xyz,
                                                                 const float *__restrict__ xyz, int N, int M,
-                                                                float radius2, int nsample,
+                                                                float radius, float radius2, int nsample,
                                                                 const BqGrid *__restrict__ grids,
                                                                 const int *__restrict__ cell_start,
                                                                 const float4 *__restrict__ sorted_pts,
@@ -254,15 +254,24 @@ __global__ void __launch_bounds__(BQG_THREADS) bqg_query_kernel(const float *__r
   const float4 *pts = sorted_pts + (size_t)b * N;
   const float *Q = new_xyz + ((size_t)b * M + j) * 3;
   const float qx = __ldg(Q), qy = __ldg(Q + 1), qz = __ldg(Q + 2);
-  const int cx = bqg_axis_cell(qx, G.minx, G.inv_h, G.gx);
-  const int cy = bqg_axis_cell(qy, G.miny, G.inv_h, G.gy);
-  const int cz = bqg_axis_cell(qz, G.minz, G.inv_h, G.gz);
-  const int x0 = max(cx - 1, 0), x1 = min(cx + 1, G.gx - 1);
+  // Candidate cells: [cell(q - r'), cell(q + r')] per axis with r' a hair above the radius.  bqg_axis_cell is a
+  // monotone function of the coordinate (fp32 subtraction, multiplication by a positive number and floor all are),
+  // and every hit has |p.x - q.x| <= |p - q| < r (1 + ~1e-7), so its cell lies inside that range WHATEVER the
+  // rounding of the cell arithmetic -- also for clouds spanning hundreds of cells, where "own cell +- 1" could miss a
+  // neighbour two cells away (round-1 advisor finding).  The slack covers the rounding of q -+ r' itself.
+  const float rx = fmaf(fabsf(qx), 4e-7f, radius * 1.0001f), ry = fmaf(fabsf(qy), 4e-7f, radius * 1.0001f),
+              rz = fmaf(fabsf(qz), 4e-7f, radius * 1.0001f);
+  const int x0 = max(bqg_axis_cell(qx - rx, G.minx, G.inv_h, G.gx), 0),
+            x1 = min(bqg_axis_cell(qx + rx, G.minx, G.inv_h, G.gx), G.gx - 1);
+  const int y0 = max(bqg_axis_cell(qy - ry, G.miny, G.inv_h, G.gy), 0),
+            y1 = min(bqg_axis_cell(qy + ry, G.miny, G.inv_h, G.gy), G.gy - 1);
+  const int z0 = max(bqg_axis_cell(qz - rz, G.minz, G.inv_h, G.gz), 0),
+            z1 = min(bqg_axis_cell(qz + rz, G.minz, G.inv_h, G.gz), G.gz - 1);
   int cnt = 0;
   bool overflow = false;
   if (x0 <= x1) {
-    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, G.gz - 1); ++zz) {
-      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, G.gy - 1); ++yy) {
+    for (int zz = z0; zz <= z1; ++zz) {
+      for (int yy = y0; yy <= y1; ++yy) {
         const int rowbase = (zz * G.gy + yy) * G.gx;
         const int beg = __ldg(cs + rowbase + x0), end = __ldg(cs + rowbase + x1 + 1);
         for (int t0 = beg; t0 < end; t0 += 32) {
@@ -361,7 +370,7 @@ extern "C" int spc_ball_query_ex(const float *new_xyz, const float *xyz, int B, 
     SPC_CUDA(cudaFuncSetAttribute(bqg_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q_smem));
   const float radius2 = radius * radius;   // f32 product, as ball_query_gpu.cu:22
   bqg_query_kernel<<<dim3(ceil_div(M, BQG_THREADS / 32), B), BQG_THREADS, q_smem, stream>>>(
-      new_xyz, xyz, N, M, radius2, nsample, grids, cell_start, sorted_pts, idx);
+      new_xyz, xyz, N, M, radius, radius2, nsample, grids, cell_start, sorted_pts, idx);
   SPC_LAUNCH_CHECK("bqg_query_kernel");
   return SPC_OK;
 }

@@ -242,6 +242,25 @@ def interp_cases():
     return c
 
 
+def ball_query_extra_cases():
+    """Ball-query cases without golden vectors (checked against the oracle and the live reference ext): long thin
+    clouds whose uniform grid has many hundreds of cells along one axis, where the fp32 cell arithmetic is least
+    accurate (round-1 advisor finding), also far away from the origin."""
+    rng = np.random.default_rng(909)
+    c = {}
+    for name, (length, off, r) in {"corridor_900_cells": (180.0, 0.0, 0.2), "corridor_far_from_origin": (150.0, 3000.0, 0.2),
+                                   "corridor_2000_cells": (100.0, -50.0, 0.05)}.items():
+        pts = rng.uniform(0, 1, (1, 12000, 3)).astype(np.float64)
+        pts[..., 0] = pts[..., 0] * length + off
+        pts[..., 1] *= 0.6
+        pts[..., 2] *= 0.3
+        xyz = pts.astype(np.float32)
+        new = np.ascontiguousarray(xyz[:, ::12]).copy()
+        new[:, ::3, 0] += np.float32(r * 0.999)             # centres whose ball reaches into the next cells
+        c[name] = (new, xyz, r, 16)
+    return c
+
+
 def interp_big_cases():
     """Larger interpolation shapes (no golden vectors: checked against the oracle and the live reference ext):
     FP2's, config 5's x4 cloud, and a ragged one (n % 4 != 0, channel count not a multiple of the tile)."""

@@ -189,6 +189,19 @@ def test_fps_prefix_property(ext):
     np.testing.assert_array_equal(idx2[0], np.arange(1024, dtype=np.int32))
 
 
+@pytest.mark.parametrize("name", list(cases.ball_query_extra_cases().keys()))
+def test_ball_query_long_thin_clouds(ext, ref_ext, name):
+    """Grids with 750-2000 cells along one axis (and clouds 3 km from the origin): the candidate range comes from the
+    monotone cell function applied to q -+ r, so no neighbour can be missed whatever the fp32 rounding."""
+    new, xyz, r, ns = cases.ball_query_extra_cases()[name]
+    want = oracle.ball_query(new, xyz, r, ns)
+    got = ext.ball_query(cu(new), cu(xyz), r, ns).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    assert (got != 0).any()
+    if ref_ext is not None:
+        np.testing.assert_array_equal(got, ref_ext.ball_query(cu(new), cu(xyz), r, ns).cpu().numpy())
+
+
 @pytest.mark.parametrize("name", list(cases.ball_query_cases().keys()))
 def test_ball_query(ext, ref_ext, name):
     new_xyz, xyz, r, ns = cases.ball_query_cases()[name]
