@@ -51,6 +51,7 @@ def _sample_centres(xyz, npoint, inds=None):
 
 
 INLINE_MAX_FEATURES = 16   # raw feature channels the fused kernel evaluates in-line (layer 0)
+PAD_TRAINING_CHANNELS = True   # training: pad 3+C grouped channels to a multiple of 4 (aligned conv GEMMs)
 
 
 def attach_pm(t, pm, pm_lo=None):
@@ -320,7 +321,14 @@ class PointnetSAModuleVotes(nn.Module):
             return new_xyz, fused, inds
         if features is not None and not features.is_contiguous():
             features = features.contiguous()      # (a caller may hand in a channel-major VIEW of a point-major cloud)
-        grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
+        # training on the GPU: zero-pad the grouped tensor to a multiple of 4 channels (aligned GEMM rows, see
+        # QueryAndGroup.forward); the first SharedMLP block pads its weight to match -- same values either way
+        pad = 4 if (self.training and xyz.is_cuda and features is not None and len(self.mlp_module) > 0
+                    and isinstance(self.grouper, pointnet2_utils.QueryAndGroup) and PAD_TRAINING_CHANNELS) else 1
+        if pad > 1:
+            grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features, pad_channels_to=pad)
+        else:
+            grouped_features, grouped_xyz = self.grouper(xyz, new_xyz, features)
         if (self.pooling == 'max' and self.training and grouped_features.is_cuda and len(self.mlp_module) > 0
                 and pt_utils.FUSED_BN_RELU_TRAINING):
             # training: the last block's BatchNorm + ReLU + max-pool run as one kernel pair (csrc/bn_relu.cu)

@@ -146,8 +146,12 @@ class QueryAndGroup(nn.Module):
         if self.ret_unique_cnt:
             assert self.sample_uniformly
 
-    def forward(self, xyz, new_xyz, features=None):
-        """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) -> (B,3+C,npoint,nsample)"""
+    def forward(self, xyz, new_xyz, features=None, pad_channels_to=1):
+        """xyz (B,N,3), new_xyz (B,npoint,3), features (B,C,N) -> (B,3+C,npoint,nsample).
+        pad_channels_to = 4 (an extension the SA module uses in training) appends all-zero channels so that the
+        channel count is a multiple of 4: 3 + 128 or 3 + 256 input channels make every row of the 1x1-conv GEMMs
+        that follow 4 bytes short of 16-byte alignment, which sends cuDNN / cuBLAS to their slow `align1` kernels
+        (14 % of a training step); the consumer pads its weight with matching zero columns."""
         if self.sample_uniformly:
             # the reference prints and exit(1)s here (:337-339); raise instead of killing the process
             raise NotImplementedError("sample_uniformly is a dead path in the reference")
@@ -158,8 +162,14 @@ class QueryAndGroup(nn.Module):
             grouped_xyz /= self.radius
         if features is not None:
             grouped_features = grouping_operation(features, idx)
-            new_features = torch.cat([grouped_xyz, grouped_features], dim=1) if self.use_xyz \
-                else grouped_features
+            if self.use_xyz:
+                parts = [grouped_xyz, grouped_features]
+                extra = -(3 + grouped_features.shape[1]) % max(int(pad_channels_to), 1)
+                if extra:
+                    parts.append(grouped_xyz.new_zeros((grouped_xyz.shape[0], extra) + tuple(grouped_xyz.shape[2:])))
+                new_features = torch.cat(parts, dim=1)
+            else:
+                new_features = grouped_features
         else:
             assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
             new_features = grouped_xyz

@@ -8,6 +8,7 @@ child `bn`) and `activation`, so keys read `...layer0.conv.weight`, `...layer0.b
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 # Training mode: run BatchNorm2d + ReLU of a conv block through the fused sm_100a kernels (csrc/bn_relu.cu)
 # instead of cuDNN batch-norm + a separate ReLU pass.  Same parameters, buffers and results (fp32, within
@@ -126,9 +127,18 @@ class _ConvBase(nn.Sequential):
     def forward(self, x, max_pool_last_dim=False):
         """max_pool_last_dim=True additionally takes the max over the last axis (the SA module's
         F.max_pool2d(kernel=[1, nsample]) + squeeze) and returns (B, C, npoint)."""
+        conv = getattr(self, self._conv_name)
+        if x.shape[1] > conv.in_channels:
+            # the caller appended all-zero channels for 16-byte-aligned GEMM rows (QueryAndGroup pad_channels_to):
+            # the same convolution with matching zero weight columns; autograd slices the weight gradient back
+            extra = x.shape[1] - conv.in_channels
+            w = F.pad(conv.weight, (0, 0) * (conv.weight.dim() - 2) + (0, extra))
+            run_conv = lambda t: F.conv2d(t, w, conv.bias, conv.stride, conv.padding)   # noqa: E731
+        else:
+            run_conv = conv
         if self._fused_training_ok(x):
             bn = getattr(self, self._bn_name)[0]
-            y = getattr(self, self._conv_name)(x)
+            y = run_conv(x)
             if y.is_contiguous() and y.shape[0] * y.shape[1] <= 65535:
                 args = (y, bn.weight, bn.bias, bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps))
                 if max_pool_last_dim and y.dim() == 4 and y.shape[3] in (16, 32, 64):
@@ -141,6 +151,10 @@ class _ConvBase(nn.Sequential):
                     bn.num_batches_tracked.add_(1)
                 return out
             out = torch.relu_(getattr(self, self._bn_name)(y))
+        elif run_conv is not conv:
+            out = x
+            for name, mod in self.named_children():
+                out = run_conv(out) if name == self._conv_name else mod(out)
         else:
             out = super().forward(x)
         return _max_pool_last(out) if max_pool_last_dim else out
