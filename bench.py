@@ -337,26 +337,45 @@ def timed_loop(step_fn, steps, warmup, flush, barrier, sampler=None):
 def hbm_bound_ops(pc, flush, hbm_peak):
     """The HBM-bound point ops the north_star sets a roofline target for, timed live on BASELINE shapes (they are not
     launched by the eval forward, where the fused SA kernel replaces grouping): grouping forward at config 4's SA1
-    shape (132 channels) and at SA2's, three_interpolate at FP2's.  CUDA events around 10 launches with an L2 flush
-    before each; algorithmic bytes = SURVEY 8(d) formulas."""
+    shape (132 channels) and at SA2's, three_interpolate at FP2's and at config 5's x4 shape.  Graph-timed with an L2
+    flush before every call (see `timed`); algorithmic bytes = SURVEY 8(d) formulas."""
     from spacap3d_b200 import _ext
     xyz = pc[:, :, :3].contiguous()
     B, N = xyz.shape[0], xyz.shape[1]
     out = []
 
-    def timed(fn, reps=10):
+    def timed(fn, reps=8):
+        """Launch-overhead-free time of one call: [L2 flush, fn] x reps captured in one CUDA graph, minus the same graph
+        without fn (these ops take 5-150 us; an eager launch adds ~5 us of host gap to every one of them)."""
         for _ in range(3):
             fn()
-        ts = []
-        for _ in range(reps):
-            flush()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return statistics.median(ts)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+
+        def capture(with_fn):
+            g = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    flush()
+                    if with_fn:
+                        fn()
+            return g
+
+        def run(g):
+            ts = []
+            for _ in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return statistics.median(ts)
+
+        ga, gb = capture(True), capture(False)
+        run(ga), run(gb)
+        return max(run(ga) - run(gb), 1e-6) / reps
 
     _, c1 = _ext.furthest_point_sampling_with_xyz(xyz, 2048)
     _, c2 = _ext.furthest_point_sampling_with_xyz(c1, 1024)
@@ -378,7 +397,18 @@ def hbm_bound_ops(pc, flush, hbm_peak):
     nbytes = 4 * B * (256 * 512 + 6 * 1024 + 256 * 1024)
     out.append({"op": "three_interpolate FP2", "shape": [B, 256, 512, 1024], "ms": round(ms, 4), "algo_bytes": nbytes,
                 "gbs": round(nbytes / ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ms / 1e6 / hbm_peak, 3),
-                "note": "9.6 MB per call: launch-latency-bound, not bandwidth-bound"})
+                "note": "12.8 MB per call: a few microseconds, latency-bound at the detector's own size"})
+    # config 5's x4 cloud: 4096 unknown <- 2048 known points per scene
+    _, u4 = _ext.furthest_point_sampling_with_xyz(xyz, 4096)
+    k4 = u4[:, :2048].contiguous()
+    _, idx4 = _ext.three_nn(u4, k4)
+    w4 = torch.rand(B, 4096, 3, device=pc.device)
+    feats4 = torch.randn(B, 256, 2048, device=pc.device)
+    ms = timed(lambda: _ext.three_interpolate(feats4, idx4, w4))
+    nbytes = 4 * B * (256 * 2048 + 6 * 4096 + 256 * 4096)
+    out.append({"op": "three_interpolate config-5 x4 shape", "shape": [B, 256, 2048, 4096], "ms": round(ms, 4),
+                "algo_bytes": nbytes, "gbs": round(nbytes / ms / 1e6, 1),
+                "frac_of_hbm_peak": round(nbytes / ms / 1e6 / hbm_peak, 3)})
     return out
 
 
@@ -655,8 +685,9 @@ def run_ours(args):
                 "algo": "bucketed (Hilbert-sorted points parked in L2, one 512-thread CTA per scene)",
                 "single_call_ms": round(statistics.median(ts), 4),
                 "us_per_round": round(statistics.median(ts) * 1e3 / max(big[0][4][3] - 1, 1), 4),
-                "why": "2.5x the latency of the cluster kernel but 1/6 of its instructions and 1/8 of its SM-time: with "
-                       "32 batches in flight the pipeline is bound by issue slots, not by one call's latency"}
+                "why": "2.5x the latency of the cluster kernel but 1/5 of its instructions and 1/3 of its SM-time "
+                       "(profiles/r2_fps_ncu.txt): with 32 batches in flight the pipeline is bound by issue slots, not by "
+                       "one call's latency"}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
