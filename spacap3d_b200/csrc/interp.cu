@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(NN_THREADS) three_nn_kernel(const float *__res
 //  * backward: a CTA owns TI_CT whole rows of grad_points in shared memory, sweeps all n positions and flushes the
 //    rows once -- no global atomics, no pre-zeroing.  Measured and NOT kept (round 2): inverting the relation into
 //    per-known-point lists (atomic-free, bit-reproducible) -- list build 39 us + gather kernel 105 us at config 5's
-//    x4 shape against 96 us for this kernel, and 29 vs 16 us at FP1's.
+//    x4 shape against 96 us for this kernel, and 29 vs 16 us at FP1's; and warp-owned channels with
+//    __match_any pre-combining and plain load-add-store (no atomics at all): 42 / 75 / 265 us against 16 / 28 / 96 --
+//    one dependent shared-memory round trip per update and warp is slower than 256 independent CAS chains.
 // ------------------------------------------------------------------------------------------------
 constexpr int TI_THREADS = 256;
 
