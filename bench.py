@@ -719,6 +719,11 @@ def run_ours(args):
                     "ms_per_step": round(e2e_s / e2e_steps_in_region * 1e3, 4)},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
+            "fast_path_check": {
+                "fused_sa_launches_per_step": ops.get("sa_fused_forward_ex", {}).get("launches_per_step", 0),
+                "expected": 5, "pm_linear_launches_per_step": ops.get("pm_linear", {}).get("launches_per_step", 0),
+                "note": "5 fused set-abstraction launches (SA1-4 + vote aggregation) and 14 pm_linear layers per forward: "
+                        "anything less means a layer fell back to the unfused kernels (a RuntimeWarning says which)"},
             "roofline": roofline, "dominant": dominant, "hbm_ops": hbm_ops, "ops": ops,
             "kernel_ms_per_step": round(step_ms_kernels, 4),
             "eager": eager,

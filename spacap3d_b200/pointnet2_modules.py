@@ -84,7 +84,9 @@ def get_pm(t):
 # dict, which would make every replica (one per device and thread) share and overwrite one cache object.
 # Keyed weakly by module, so a replica's cache dies with the replica.
 import threading as _threading
+import warnings
 import weakref as _weakref
+_WARNED_UNFUSED = _weakref.WeakSet()
 _CACHES = _weakref.WeakKeyDictionary()
 _CACHES_LOCK = _threading.Lock()
 
@@ -395,7 +397,13 @@ class PointnetSAModuleVotes(nn.Module):
                 out, out_pm = _ext.sa_fused_forward(xyz, new_xyz, idx, cache.w0x(W0), b0, W1, b1, W2, b2,
                                                     G=G, radius=radius, want_point_major=True)
             return attach_pm(out, out_pm)       # lets the next layer skip its transpose + cast
-        except _lib.SpcUnsupported:
+        except _lib.SpcUnsupported as e:
+            # not an error -- the unfused kernels give the same result -- but never silent: a configuration that
+            # falls off the fused path is 10-20x slower in this layer
+            if self not in _WARNED_UNFUSED:
+                _WARNED_UNFUSED.add(self)
+                warnings.warn("PointnetSAModuleVotes: no fused set-abstraction kernel for this layer (%s); using the "
+                              "unfused kernels" % e, RuntimeWarning, stacklevel=3)
             return None
 
 
