@@ -64,24 +64,25 @@ __device__ __forceinline__ void mbarrier_wait(uint64_t *bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
-// same, but yields the issue slot between polls (producer / epilogue warps share their SM
-// sub-partitions with each other; a tight spin stole 30 % of the issue slots, ncu)
+// same, for the producer / epilogue warps, which share their SM sub-partitions with each other: a tight spin stole
+// 25-30 % of the issue slots (ncu, round 1) and a nanosleep back-off still spent ~15 % of the kernel's instructions
+// on polling (SYNCS + NANOSLEEP + their branches, round 2) -- and the whole pipeline is issue-slot bound.  try_wait
+// with a suspend-time hint parks the thread in hardware until the phase completes (it wakes at once) or the hint
+// expires: a handful of polls per wait, no wake-up delay.
 __device__ __forceinline__ void mbarrier_wait_relaxed(uint64_t *bar, unsigned parity) {
-  unsigned done, ns = 32;
+  unsigned done;
   for (;;) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(s2u(bar)), "r"(parity)
+        : "r"(s2u(bar)), "r"(parity), "r"(20000u)
         : "memory");
     if (done) break;
-    __nanosleep(ns);
-    if (ns < 256) ns <<= 1;          // 32, 64, 128, 256 ns: the stages are double-buffered, so a late
-  }                                  // wake-up costs nothing, a tight spin costs issue slots (25 %, ncu)
+  }
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

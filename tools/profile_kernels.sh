@@ -14,6 +14,6 @@ prof bqg_query 'bqg_query_kernel' 2 python tools/bench_ops.py --ops ball_query -
 prof fps_cluster 'fps_cluster_kernel' 2 python tools/time_fps.py --algos cluster --streams 1
 prof fps_bucket 'fps_bucket_kernel' 2 python tools/time_fps.py --algos bucket --streams 1
 prof pm_linear 'pm_linear_kernel' 30 python tools/one_forward.py
-prof sa_fused_sa2 'sa_fused_pipe_kernel<\(int\)128, \(int\)128, \(int\)256, \(int\)32' 2 python tools/one_forward.py --default-options
-prof sa_fused_sa1 'sa_fused_pipe_kernel<\(int\)64' 2 python tools/one_forward.py --default-options
+prof sa_fused_sa2 'sa_fused_pipe_kernel' 16 python tools/one_forward.py --default-options
+prof sa_fused_sa1 'sa_fused_pipe_kernel' 15 python tools/one_forward.py --default-options
 prof three_interpolate 'three_interpolate_kernel' 8 python tools/bench_ops.py --ops interp --no-ref --iters 3
