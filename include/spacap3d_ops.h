@@ -154,8 +154,9 @@ int spc_three_interpolate_grad(const float *grad_out, const int32_t *idx, const 
  * 3 x [1x1 conv, BN, ReLU]) and pointnet2_modules.py:256-271 (max-pool over nsample)).
  *   xyz (B,n,3), new_xyz (B,npoint,3), idx (B,npoint,nsample) from spc_ball_query.
  *   Layer 0, one of two forms (BatchNorm folded into weights/bias by the caller):
- *     in-line  : G_f16 == NULL; feat (B,Cf,n) raw features (Cf <= 16, NULL when Cf == 0),
- *                W0 (C1,3+Cf), b0 (C1);  h1 = relu(W0 . [(p-c)/radius, f] + b0)
+ *     in-line  : G_f16 == NULL; feat (B,Cf,n) raw features (Cf <= 13, NULL when Cf == 0),
+ *                W0 (C1,3+Cf), b0 (C1);  h1 = relu(W0 . [(p-c)/radius, f] + b0), on the tensor cores with
+ *                inputs and weights as fp16 (hi, lo) pairs and three partial products: fp32-grade
  *     projected: G_f16 (B,n,C1) FP16 = W0[:,3:] . f per POINT (one plain GEMM by the caller, conv0 is
  *                linear), Cf == 0, W0 (C1,3) = the xyz columns, b0 (C1);
  *                h1 = relu(G[idx] + W0 . (p-c)/radius + b0), the xyz term evaluated in fp32 here
@@ -171,10 +172,8 @@ int spc_sa_fused_forward(const float *xyz, const float *new_xyz, const int32_t *
                          int Cf, float radius, const void *W1_f16, const float *b1,
                          const void *W2_f16, const float *b2, int B, int n, int npoint, int nsample,
                          int C1, int C2, int C3, float *out, void *out_pm_f16, void *stream);
-/* Same, plus optional HOST copies of the folded layer-0 weights (W0_host (C1,3+Cf), b0_host (C1); host memory, read
- * during the call; NULL = not available).  In the in-line form with C1*(4+Cf) <= 768 the kernel then takes them by
- * value through its parameters (constant bank) instead of staging W0 in shared memory.  Results are the same up to
- * fp32 summation order (the bias is the first addend instead of the last).
+/* Same, with a per-call launch hint.  W0_host / b0_host (host copies of the folded layer-0 weights, or NULL) fed a
+ * constant-bank FFMA path that no longer exists: they are accepted and ignored.
  * min_tiles_per_cta: PER-CALL launch hint (0 = one CTA per SM, the latency optimum): give every CTA at least this
  * many 128-row tiles, i.e. launch fewer CTAs for the small layers.  Results do not change.  With several batches in
  * flight the freed SMs run other streams' kernels: +4.5 % scenes/s at 16 on B200 (12 streams), -6 % for one stream. */

@@ -50,7 +50,7 @@ def _sample_centres(xyz, npoint, inds=None):
     return new_xyz, inds
 
 
-INLINE_MAX_FEATURES = 16   # raw feature channels the fused kernel evaluates in-line (layer 0)
+INLINE_MAX_FEATURES = 13   # raw feature channels the fused kernel evaluates in-line (layer 0)
 PAD_TRAINING_CHANNELS = True   # training: pad 3+C grouped channels to a multiple of 4 (aligned conv GEMMs)
 
 

@@ -16,6 +16,9 @@ LAYERS = {
     "sa1_xyz_height": (8192, 1, 512, 0.2, 64, [1, 64, 64, 128]),
     "sa1_xyz_only": (8192, 0, 512, 0.2, 64, [0, 64, 64, 128]),
     "sa1_rgb_normal_height": (8192, 7, 256, 0.2, 64, [7, 64, 64, 128]),
+    "sa1_9ch_late_features": (4096, 9, 256, 0.2, 64, [9, 64, 64, 128]),       # in-line: 3 K steps, feature 8 read late
+    "sa1_13ch_max_inline": (4096, 13, 256, 0.2, 32, [13, 64, 64, 128]),       # in-line: 4 K steps, the most it takes
+    "sa1_14ch_projected": (4096, 14, 256, 0.2, 64, [14, 64, 64, 128]),        # one more channel: projected form
     "sa1_multiview": (4096, 132, 256, 0.3, 64, [132, 64, 64, 128]),
     "sa2": (2048, 128, 1024, 0.4, 32, [128, 128, 128, 256]),
     "sa3": (1024, 256, 512, 0.8, 16, [256, 128, 128, 256]),
