@@ -679,6 +679,132 @@ static int launch_group_grad_csr(const float *grad_out, const int *offsets, cons
   return SPC_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Large clouds (N > 8192: the input level of the detector, e.g. C = 132 multiview features over 40 k points).
+// Staging position partitions does not pay here: a partition of <= 24 576 positions touches a small, different
+// subset of the N points, so every (channel, partition) CTA walked all N offsets for a few thousand hits and
+// combined its partial sums with global atomics (2.45 ms for 727 MB at C = 132, 4.5 % of HBM, round 1).
+// Point-owned gather instead: ONE list per point over all positions (32-bit positions, built with warp-aggregated
+// atomic cursors: three launches of a few microseconds; the order inside a list is not deterministic, the sum is
+// within fp32 rounding), a thread owns a point and CT = 8 channels, reads its positions once and gathers the 8
+// rows of grad_out straight from global memory (each row is read exactly once overall; it stays in L2 while the
+// CTAs of its (scene, channel tile) run), and writes its 8 results with coalesced stores.  No floating-point
+// atomics, no memset.
+// ----------------------------------------------------------------------------------------------
+constexpr int GL_THREADS = 256;
+constexpr int GL_CT = 8;
+constexpr int GL_LONG = 48;          // lists longer than this are summed by a whole warp
+constexpr int GL_LONG_CAP = 256;
+
+// counts[b][1 + idx[b,t]] += 1, one atomic per distinct index of a warp (the ball-query padding repeats one index)
+__global__ void gl_hist_kernel(const int32_t *__restrict__ idx, int N, int S, int Np, int *__restrict__ offsets) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = t < S;
+  const int i = ok ? __ldg(idx + (size_t)b * S + t) : -1;
+  const bool valid = ok && (unsigned)i < (unsigned)N;
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? i : -1 - (int)lane_id());
+  if (valid && (peers & ((1u << lane_id()) - 1u)) == 0u) atomicAdd(offsets + (size_t)b * Np + 1 + i, __popc(peers));
+}
+
+// order[b][offsets[b][i] + k] = k-th position (in arrival order) that references point i
+__global__ void gl_fill_kernel(const int32_t *__restrict__ idx, int N, int S, int Np, const int *__restrict__ offsets,
+                               int *__restrict__ cursor, int32_t *__restrict__ order) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = t < S;
+  const int i = ok ? __ldg(idx + (size_t)b * S + t) : -1;
+  const bool valid = ok && (unsigned)i < (unsigned)N;
+  const unsigned lane = lane_id();
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? i : -1 - (int)lane);
+  const unsigned before = peers & ((1u << lane) - 1u);
+  int base = 0;
+  if (valid && before == 0u) base = atomicAdd(cursor + (size_t)b * Np + i, __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+  if (valid) order[(size_t)b * S + __ldg(offsets + (size_t)b * Np + i) + base + __popc(before)] = t;
+}
+
+__global__ void __launch_bounds__(GL_THREADS) group_points_grad_gather_kernel(
+    const float *__restrict__ grad_out, const int *__restrict__ offsets, const int32_t *__restrict__ order, int C,
+    int N, int S, int Np, float *__restrict__ grad_points) {
+  __shared__ int s_long[GL_LONG_CAP];
+  __shared__ int s_nlong;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * GL_CT;
+  const int ct = min(GL_CT, C - c0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * GL_THREADS + tid;
+  const float *g = grad_out + ((size_t)b * C + c0) * S;
+  const int *off = offsets + (size_t)b * Np;
+  const int32_t *ord = order + (size_t)b * S;
+  float *dst = grad_points + ((size_t)b * C + c0) * N;
+  if (tid == 0) s_nlong = 0;
+  __syncthreads();
+  if (i < N) {
+    const int o0 = __ldg(off + i), o1 = __ldg(off + i + 1);
+    bool mine = true;
+    if (o1 - o0 > GL_LONG) {
+      const int q = atomicAdd(&s_nlong, 1);
+      if (q < GL_LONG_CAP) { s_long[q] = i; mine = false; }
+    }
+    if (mine) {
+      float acc[GL_CT];
+#pragma unroll
+      for (int r = 0; r < GL_CT; ++r) acc[r] = 0.f;
+      int k = o0;
+      for (; k + 2 <= o1; k += 2) {                      // two positions x 8 rows = 16 independent loads in flight
+        const int q0 = __ldg(ord + k), q1 = __ldg(ord + k + 1);
+        float v0[GL_CT], v1[GL_CT];
+#pragma unroll
+        for (int r = 0; r < GL_CT; ++r) {
+          v0[r] = r < ct ? __ldg(g + (size_t)r * S + q0) : 0.f;
+          v1[r] = r < ct ? __ldg(g + (size_t)r * S + q1) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < GL_CT; ++r) acc[r] = (acc[r] + v0[r]) + v1[r];
+      }
+      if (k < o1) {
+        const int q0 = __ldg(ord + k);
+#pragma unroll
+        for (int r = 0; r < GL_CT; ++r) acc[r] += r < ct ? __ldg(g + (size_t)r * S + q0) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < GL_CT; ++r)
+        if (r < ct) dst[(size_t)r * N + i] = acc[r];
+    }
+  }
+  __syncthreads();
+  // ---- long lists (hubs of the ball-query padding): one warp per point ---------------------------------------
+  const int nlong = min(s_nlong, GL_LONG_CAP);
+  for (int q = warp; q < nlong; q += GL_THREADS / 32) {
+    const int pi = s_long[q];
+    const int o0 = __ldg(off + pi), o1 = __ldg(off + pi + 1);
+    float acc[GL_CT];
+#pragma unroll
+    for (int r = 0; r < GL_CT; ++r) acc[r] = 0.f;
+    for (int k = o0 + lane; k < o1; k += 32) {
+      const int qq = __ldg(ord + k);
+#pragma unroll
+      for (int r = 0; r < GL_CT; ++r) acc[r] += r < ct ? __ldg(g + (size_t)r * S + qq) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < GL_CT; ++r)
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < GL_CT; ++r)
+        if (r < ct) dst[(size_t)r * N + pi] = acc[r];
+    }
+  }
+}
+
+// workspace of the large-cloud path: offsets (B, Np) + cursors (B, Np) + order (B, S), all int32
+static size_t gl_workspace_bytes(int B, int N, long long S) {
+  const size_t Np = ((size_t)N + 1 + 3) / 4 * 4;
+  return 2 * (size_t)B * Np * sizeof(int) + (size_t)B * (size_t)S * sizeof(int32_t);
+}
+
 }  // namespace spc
 
 using namespace spc;
@@ -778,6 +904,7 @@ extern "C" size_t spc_group_points_grad_workspace_bytes(int B, int N, int npoint
   if (B <= 0 || N <= 0 || npoint <= 0 || nsample <= 0) return 0;
   const long long S = (long long)npoint * nsample;
   if (S >= (1LL << 31)) return 0;
+  if (N > GB_MAX_N) return gl_workspace_bytes(B, N, S);
   const GradPlan g = plan_group_grad(1, N, (int)S);
   // offsets (B,H,Np) int32  +  order (B,S) uint16, both starting 16-byte aligned
   return (size_t)B * g.H * (size_t)g.Np * sizeof(int) + (((size_t)B * (size_t)S * sizeof(uint16_t) + 15) & ~(size_t)15);
@@ -791,14 +918,30 @@ extern "C" int spc_group_points_grad_ex(const float *grad_out, const int32_t *id
   SPC_CHECK_ARG(S64 < (1LL << 31), "group_points_grad: npoint*nsample overflows int32");
   const int S = (int)S64;
   const size_t need = spc_group_points_grad_workspace_bytes(B, N, npoint, nsample);
-  // The list build costs ~N*S/1024 warp-iterations per scene and is shared by all C channels: worth it
-  // once C is a few channels and the cloud is not huge relative to C (SA2-SA4, vote aggregation,
-  // multiview SA1); otherwise the atomic kernel is faster.
+  // The list build is shared by all C channels: worth it once C is a few channels (SA2-SA4, vote aggregation,
+  // every input level with features); with fewer the atomic kernel is faster.
   if (!workspace || need == 0 || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15) || C < 4 ||
-      (long long)N > 512LL * C || B == 0 || B > 65535)
+      (N <= GB_MAX_N && (long long)N > 512LL * C) || B == 0 || B > 65535)
     return spc_group_points_grad(grad_out, idx, B, C, N, npoint, nsample, grad_points, stream_);
   SPC_CHECK_ARG(grad_points && grad_out && idx, "group_points_grad: null pointer");
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (N > GB_MAX_N) {
+    // large cloud: one list per point over all positions, point-owned gather (see group_points_grad_gather_kernel)
+    const size_t Np = ((size_t)N + 1 + 3) / 4 * 4;
+    int *offsets = reinterpret_cast<int *>(workspace);
+    int *cursor = offsets + (size_t)B * Np;
+    int32_t *order = cursor + (size_t)B * Np;
+    SPC_CUDA(cudaMemsetAsync(offsets, 0, 2 * (size_t)B * Np * sizeof(int), stream));
+    gl_hist_kernel<<<dim3(ceil_div(S, 256), B), 256, 0, stream>>>(idx, N, S, (int)Np, offsets);
+    gg_scan_kernel<<<B, 1024, 0, stream>>>(N, (int)Np, offsets);
+    gl_fill_kernel<<<dim3(ceil_div(S, 256), B), 256, 0, stream>>>(idx, N, S, (int)Np, offsets, cursor, order);
+    SPC_LAUNCH_CHECK("group_points_grad list build (large cloud)");
+    SPC_CHECK_ARG(ceil_div(C, GL_CT) <= 65535, "group_points_grad: too many channel tiles");
+    group_points_grad_gather_kernel<<<dim3(ceil_div(N, GL_THREADS), ceil_div(C, GL_CT), B), GL_THREADS, 0, stream>>>(
+        grad_out, offsets, order, C, N, S, (int)Np, grad_points);
+    SPC_LAUNCH_CHECK("group_points_grad_gather_kernel");
+    return SPC_OK;
+  }
   const GradPlan g = plan_group_grad(C, N, S);
   SPC_CHECK_ARG(ceil_div(C, g.CT) <= 65535 && g.H <= 65535, "group_points_grad: grid too large");
   int *offsets = reinterpret_cast<int *>(workspace);

@@ -223,6 +223,9 @@ def group_grad_big_cases():
     c["three_partitions"] = (padded(1, 3000, 1000, 60, 100), 4, 3000)             # S=60000 -> H=3
     c["odd_unaligned"] = (padded(2, 333, 77, 13, 5), 5, 333)                      # S=1001: no bulk copy
     c["one_hub"] = (np.zeros((1, 64, 16), np.int32) + 7, 6, 50)                   # every position -> point 7
+    # N > 8192: one list per point over all positions + point-owned gather (atomic cursors: order not deterministic)
+    c["large_cloud"] = (padded(2, 20000, 512, 64, 300), 9, 20000)                 # S=32768, CT=8 + a 1-channel tile
+    c["large_cloud_hubs"] = (padded(1, 9000, 300, 64, 3), 8, 9000)                # four hubs with very long lists
     return c
 
 
