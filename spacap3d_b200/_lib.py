@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPC_LIB_PATH lets a developer load an instrumented build of the same library (profiling only)
 LIB_PATH = os.environ.get("SPC_LIB_PATH") or os.path.join(_HERE, "libspacap3d_ops.so")
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -44,7 +44,7 @@ SIGNATURES = {
     "spc_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "spc_three_nn_weights": [_p, _p, _i, _i, _i, _p, _p, _p],
     "spc_interp_cat_pm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
-    "spc_pm_linear": [_p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
+    "spc_pm_linear": [_p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
     "spc_sa_fused_forward": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,
                              _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "spc_sa_fused_forward_ex": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,

@@ -391,7 +391,7 @@ using namespace spc;
 extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, const void *W_hi, const void *W_lo,
                              const float *bias, int N, int mode, int points_per_scene, void *Y_hi, void *Y_lo,
                              float *out, const float *seed_cm, const float *seed_xyz, float *vote_xyz,
-                             void *stream_) {
+                             int n_tile, void *stream_) {
   // rows are K * 2 bytes apart and TMA needs 16-byte strides; K need not be a multiple of the 64-element chunk
   SPC_CHECK_ARG(M >= 0 && K >= 8 && K % 8 == 0 && K <= 4096, "pm_linear: K=%d must be a multiple of 8", K);
   SPC_CHECK_ARG(N >= 1 && N <= 272, "pm_linear: N=%d out of range (1..272)", N);
@@ -409,9 +409,13 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
                 "pm_linear: vote mode needs out, Y_hi, seed_cm, seed_xyz, vote_xyz and (N - 3) %% 32 == 0");
   PmLinearParams p;
   p.M = M; p.K = K; p.N = N;
-  // the N dimension is tiled over grid.y in slices of 128 channels (twice the CTAs, half the weight bytes each CTA
-  // streams); the vote tail needs whole rows for its L2 norm and takes all of N
-  p.NT = (mode == SPC_PM_VOTE || N <= 128) ? N : 128;
+  // the N dimension is tiled over grid.y in slices of n_tile channels (default 128: twice the CTAs for N = 256, half
+  // the weight bytes each CTA streams -- the lowest latency for a layer that runs alone; one slice per row tile
+  // loads X once and holds an SM for less time in total, which is what a saturated pipeline wants); the vote tail
+  // needs whole rows for its L2 norm and takes all of N
+  SPC_CHECK_ARG(n_tile >= 0 && n_tile % 16 == 0, "pm_linear: n_tile=%d must be 0 or a multiple of 16", n_tile);
+  const int slice = n_tile > 0 ? n_tile : 128;
+  p.NT = (mode == SPC_PM_VOTE || N <= slice) ? N : slice;
   const int n_tiles = (N + p.NT - 1) / p.NT;
   const int Nr = ((p.NT < N ? p.NT : N) + 15) / 16 * 16;      // weight rows staged per CTA
   p.has_lo = X_lo != nullptr;

@@ -19,18 +19,20 @@ class GraphedDetector:
     replays the graph and (optionally) copies the requested outputs to pinned host buffers; it
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
-    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, sa_min_tiles=16, fps_algo=None):
+    def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, sa_min_tiles=16, fps_algo=None,
+                 pm_n_tile=256):
         assert example.is_cuda
         # Launch hints baked into the captured graphs (per call and thread-local: nothing process-wide changes).
         # With several batches in flight what limits throughput is how much of the GPU the latency-bound sampler
         # holds while it runs, not how long one call takes: the bucketed sampler (a quarter of an SM per scene
-        # instead of four SMs) wherever it applies, and fewer, longer-lived CTAs for the small fused-SA layers
-        # (every CTA pays a fixed weight-staging cost).
+        # instead of four SMs) wherever it applies, fewer, longer-lived CTAs for the small fused-SA layers
+        # (every CTA pays a fixed weight-staging cost) and one CTA per row tile for the 256-wide pm_linear layers
+        # (tools/marginal_cost.py: the 14 pm_linear launches cost 77 us of a 412 us step, mostly CTA life time).
         from . import _ext
         if fps_algo is None:
             n = example.shape[1]
             fps_algo = _ext.FPS_BUCKET if _ext.FPS_BUCKET_MIN_N <= n <= _ext.FPS_BUCKET_MAX_N else _ext.FPS_AUTO
-        self._options = dict(sa_min_tiles=int(sa_min_tiles), fps_algo=int(fps_algo))
+        self._options = dict(sa_min_tiles=int(sa_min_tiles), fps_algo=int(fps_algo), pm_n_tile=int(pm_n_tile))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)

@@ -89,3 +89,21 @@ def test_argument_checks():
     with pytest.raises(_lib.SpcError):
         _ext.pm_linear(X[:, :44].contiguous(), (W[0][:, :44].contiguous(), W[1][:, :44].contiguous()), b,
                        _ext.PM_HIDDEN, 256)          # K not a multiple of 8
+
+
+def test_n_tile_hint_does_not_change_results():
+    """The per-call launch hint (output channels per CTA) only changes the grid: 256-wide layers in one CTA per row
+    tile, in two 128-channel slices (default) or in four 64-channel slices give the same bits."""
+    from spacap3d_b200 import _ext
+    M = 384
+    X, W, b, _ = _layer(M, 256, 256, 21, True)
+    outs = []
+    for nt in (0, 64, 256):
+        with _ext.launch_options(pm_n_tile=nt):
+            y_hi, y_lo = _ext.pm_linear(X, W, b, _ext.PM_HIDDEN, M)
+        outs.append((y_hi.clone(), y_lo.clone()))
+    for y_hi, y_lo in outs[1:]:
+        assert torch.equal(y_hi, outs[0][0]) and torch.equal(y_lo, outs[0][1])
+    with pytest.raises(RuntimeError):
+        with _ext.launch_options(pm_n_tile=100):                  # not a multiple of 16
+            _ext.pm_linear(X, W, b, _ext.PM_HIDDEN, M)
