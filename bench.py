@@ -510,7 +510,9 @@ def run_ours(args):
     if args.mode == "graph":
         # ---- (1b) headline: CUDA-graph replay, N_STREAMS batches in flight ------------------------
         from spacap3d_b200.pipeline import GraphedDetector
-        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS)
+        tune = {k: v for k, v in (("pm_n_tile", args.pm_n_tile), ("sa_min_tiles", args.sa_min_tiles),
+                                        ("pm_tiles_per_cta", args.pm_tiles_per_cta)) if v is not None}
+        runner = GraphedDetector(model, resident[0], n_streams=N_STREAMS, result_keys=RESULT_KEYS, **tune)
 
         def timed_graph(submit, steps, warmup, repeats, sampler=None):
             """`repeats` timed regions of exactly `steps` submits each, every region bracketed by a barrier +
@@ -1084,6 +1086,9 @@ def main():
     ap.add_argument("--points", type=int, default=N_POINTS, help="points per scene (config 5: 40000..200000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=N_STREAMS, help="graph replay streams (batches in flight)")
+    ap.add_argument("--pm-n-tile", type=int, default=None, help="tuning: pm_linear output channels per CTA in the graphs")
+    ap.add_argument("--sa-min-tiles", type=int, default=None, help="tuning: fused-SA tiles per CTA in the graphs")
+    ap.add_argument("--pm-tiles-per-cta", type=int, default=None, help="tuning: pm_linear row tiles per CTA in the graphs")
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: CUDA-graph replay on %d streams (headline); eager: plain launches" % N_STREAMS)
     args = ap.parse_args()

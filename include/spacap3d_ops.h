@@ -218,7 +218,10 @@ int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float 
  *                                              vote_xyz (B,points,3) = seed_xyz + net[D:D+3]
  * n_tile: PER-CALL launch hint, 0 or a multiple of 16: output channels per CTA (0 = 128).  Results do not change.
  *   128 splits a 256-wide layer over two CTAs per row tile (lowest latency alone); 256 keeps it in one, which loads
- *   X once and occupies fewer SMs: +2 % scenes/s with 32 batches in flight on B200. */
+ *   X once and occupies fewer SMs: +2 % scenes/s with 32 batches in flight on B200.
+ * tiles_per_cta: PER-CALL launch hint (0 = 1): consecutive 128-row tiles one CTA works through.  With more than one
+ *   the accumulator is double-buffered in TMEM and the epilogue of a tile overlaps the loads of the next; fewer,
+ *   longer-lived CTAs (higher latency alone, less SM time in a saturated pipeline).  Results do not change. */
 #define SPC_PM_HIDDEN 0
 #define SPC_PM_OUT_CM 1
 #define SPC_PM_OUT_PM32 2
@@ -226,7 +229,8 @@ int spc_interp_cat_pm(const void *known_pm_f16, const int32_t *idx, const float 
 #define SPC_PM_LINEAR 4
 int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, const void *W_hi, const void *W_lo,
                   const float *bias, int N, int mode, int points_per_scene, void *Y_hi, void *Y_lo, float *out,
-                  const float *seed_cm, const float *seed_xyz, float *vote_xyz, int n_tile, void *stream);
+                  const float *seed_cm, const float *seed_xyz, float *vote_xyz, int n_tile, int tiles_per_cta,
+                  void *stream);
 
 
 /* ---- training-mode BatchNorm + ReLU of a shared-MLP block -------------------------------------------

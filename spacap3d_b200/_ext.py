@@ -59,6 +59,7 @@ class _LaunchOptions(threading.local):
     fps_algo = FPS_AUTO        # sampler selection for large clouds
     sa_min_tiles = 0           # fused SA kernel: at least this many 128-row tiles per CTA (0 = one CTA per SM)
     pm_n_tile = 0              # pm_linear: output channels per CTA (0 = 128: lowest latency; 256 = fewest CTAs)
+    pm_tiles_per_cta = 0       # pm_linear: 128-row tiles per CTA (0 = 1; > 1: double-buffered accumulator, fewer CTAs)
 
 
 _options = _LaunchOptions()
@@ -417,7 +418,7 @@ def pm_linear(X, W, bias, mode, points_per_scene, seed_cm=None, seed_xyz=None, w
     with torch.cuda.device(dev):
         _lib.call("spc_pm_linear", X_hi.data_ptr(), ptr(X_lo), M, K, W_hi.data_ptr(), W_lo.data_ptr(), bias.data_ptr(),
                   N, int(mode), int(points_per_scene), ptr(Y_hi), ptr(Y_lo), ptr(out), ptr(seed_cm), ptr(seed_xyz),
-                  ptr(vote_xyz), int(_options.pm_n_tile), _stream())
+                  ptr(vote_xyz), int(_options.pm_n_tile), int(_options.pm_tiles_per_cta), _stream())
     if mode in (PM_HIDDEN, PM_LINEAR):
         return Y_hi, Y_lo
     if mode == PM_OUT_CM:

@@ -44,7 +44,7 @@ SIGNATURES = {
     "spc_three_interpolate_grad": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "spc_three_nn_weights": [_p, _p, _i, _i, _i, _p, _p, _p],
     "spc_interp_cat_pm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p],
-    "spc_pm_linear": [_p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p],
+    "spc_pm_linear": [_p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "spc_sa_fused_forward": [_p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,
                              _i, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "spc_sa_fused_forward_ex": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p,

@@ -31,6 +31,9 @@ __device__ __forceinline__ uint32_t pl_s2u(const void *p) { return (uint32_t)__c
 __device__ __forceinline__ void pl_mbar_init(uint64_t *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pl_s2u(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void pl_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pl_s2u(bar)) : "memory");
+}
 __device__ __forceinline__ void pl_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pl_s2u(bar)), "r"(bytes) : "memory");
 }
@@ -122,6 +125,7 @@ struct PmLinearParams {
   int NT;                      // output channels per CTA (grid.y tiles of the N dimension; the vote tail takes all of N)
   int has_lo;                  // X comes as a hi + lo pair
   int stages;
+  int tiles_per_cta;           // row tiles one CTA works through (>= 1); the accumulator is double-buffered when it fits
   int mode;
   int n;                       // points per scene (channel-major outputs)
   const float *bias;           // (N)
@@ -146,7 +150,7 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
                  const PmLinearParams p) {
   extern __shared__ __align__(128) uint8_t pl_smem_raw[];
   uint8_t *smem = pl_smem_raw + ((1024u - (pl_s2u(pl_smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned
-  __shared__ __align__(8) uint64_t full[PL_MAX_STAGES], empty[PL_MAX_STAGES], acc_full;
+  __shared__ __align__(8) uint64_t full[PL_MAX_STAGES], empty[PL_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
   __shared__ float s_bias[288];
 
@@ -161,13 +165,21 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int A_BYTES = PL_ROWS * 128;
   const int B_BYTES = Nr * 128;
   const int STAGE_BYTES = A_BYTES * (1 + p.has_lo) + 2 * B_BYTES;
-  const int row0 = blockIdx.x * PL_ROWS;
   const int KCH = (p.K + PL_KC - 1) / PL_KC;           // a partial last chunk is zero-filled by TMA (both operands)
-  const uint32_t tmem_cols = Nr > 256 ? 512u : (Nr > 128 ? 256u : 128u);
+  // A CTA works through up to tiles_per_cta consecutive row tiles of its channel slice.  With more than one the
+  // accumulator is double-buffered in TMEM (2 x 128 or 2 x 256 columns; the 272-wide vote tail has one buffer), so
+  // the epilogue of tile i overlaps the loads and MMAs of tile i + 1, and the setup (barriers, TMEM allocation, bias)
+  // is paid once: a CTA's life per tile drops from setup + load + MMA + epilogue to max(load, epilogue).
+  const int num_row_tiles = (p.M + PL_ROWS - 1) / PL_ROWS;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int ntile = min(p.tiles_per_cta, num_row_tiles - tile0);
+  const int BUFC = Nr > 128 ? 256 : 128;               // accumulator columns per buffer
+  const int NBUF = (ntile > 1 && Nr <= 256) ? 2 : 1;
+  const uint32_t tmem_cols = Nr > 256 ? 512u : (uint32_t)(NBUF * BUFC);
 
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { pl_mbar_init(&full[s], 1); pl_mbar_init(&empty[s], 1); }
-    pl_mbar_init(&acc_full, 1);
+    for (int u = 0; u < 2; ++u) { pl_mbar_init(&acc_full[u], 1); pl_mbar_init(&acc_empty[u], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) pl_tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -181,17 +193,20 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // =============================== TMA PRODUCER (one thread) =====================================
     if (lane == 0) {
       const int BR = Nr > 256 ? Nr / 2 : Nr;                  // weight rows per TMA box (<= 256)
-      for (int c = 0; c < KCH; ++c) {
-        const int s = c % p.stages;
-        if (c >= p.stages) pl_mbar_wait(&empty[s], (unsigned)((c / p.stages - 1) & 1));
-        uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-        pl_mbar_expect_tx(&full[s], (unsigned)STAGE_BYTES);
-        pl_tma_load(st, &tmA_hi, c * PL_KC, row0, &full[s]);
-        uint8_t *b = st + A_BYTES;
-        if (p.has_lo) { pl_tma_load(b, &tmA_lo, c * PL_KC, row0, &full[s]); b += A_BYTES; }
-        for (int r = 0; r < Nr; r += BR) {
-          pl_tma_load(b + (size_t)r * 128, &tmB_hi, c * PL_KC, n_off + r, &full[s]);
-          pl_tma_load(b + B_BYTES + (size_t)r * 128, &tmB_lo, c * PL_KC, n_off + r, &full[s]);
+      for (int i = 0, g = 0; i < ntile; ++i) {
+        const int row0 = (tile0 + i) * PL_ROWS;
+        for (int c = 0; c < KCH; ++c, ++g) {                  // g: chunk counter over all tiles (the stage ring goes on)
+          const int s = g % p.stages;
+          if (g >= p.stages) pl_mbar_wait(&empty[s], (unsigned)((g / p.stages - 1) & 1));
+          uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+          pl_mbar_expect_tx(&full[s], (unsigned)STAGE_BYTES);
+          pl_tma_load(st, &tmA_hi, c * PL_KC, row0, &full[s]);
+          uint8_t *b = st + A_BYTES;
+          if (p.has_lo) { pl_tma_load(b, &tmA_lo, c * PL_KC, row0, &full[s]); b += A_BYTES; }
+          for (int r = 0; r < Nr; r += BR) {
+            pl_tma_load(b + (size_t)r * 128, &tmB_hi, c * PL_KC, n_off + r, &full[s]);
+            pl_tma_load(b + B_BYTES + (size_t)r * 128, &tmB_lo, c * PL_KC, n_off + r, &full[s]);
+          }
         }
       }
     }
@@ -199,9 +214,16 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     // =============================== MMA ISSUER (one thread) =======================================
     if (lane == 0) {
       const uint32_t idesc1 = pl_idesc_f16(PL_ROWS, N1), idesc2 = pl_idesc_f16(PL_ROWS, 16);
-      for (int c = 0; c < KCH; ++c) {
-        const int s = c % p.stages;
-        pl_mbar_wait(&full[s], (unsigned)((c / p.stages) & 1));
+      for (int i = 0, g = 0; i < ntile; ++i) {
+      const int buf = i % NBUF;
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * BUFC);
+      if (i >= NBUF) {                                        // the epilogue has drained this buffer (tile i - NBUF)
+        pl_mbar_wait(&acc_empty[buf], (unsigned)((i / NBUF - 1) & 1));
+        pl_tc_fence_after();
+      }
+      for (int c = 0; c < KCH; ++c, ++g) {
+        const int s = g % p.stages;
+        pl_mbar_wait(&full[s], (unsigned)((g / p.stages) & 1));
         pl_tc_fence_after();
         const uint32_t aH = pl_s2u(smem + (size_t)s * STAGE_BYTES);
         const uint32_t aL = aH + A_BYTES;
@@ -211,29 +233,32 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int kk = 0; kk < PL_KC / 16; ++kk) {
           const uint32_t ko = kk * 32;                        // 16 fp16 = 32 bytes inside the 128-byte atom
           const uint32_t acc = (c > 0 || kk > 0) ? 1u : 0u;
-          pl_umma_f16(tmem_base, pl_smem_desc(aH + ko), pl_smem_desc(bH + ko), idesc1, acc);
-          pl_umma_f16(tmem_base, pl_smem_desc(aH + ko), pl_smem_desc(bL + ko), idesc1, 1u);
-          if (p.has_lo) pl_umma_f16(tmem_base, pl_smem_desc(aL + ko), pl_smem_desc(bH + ko), idesc1, 1u);
+          pl_umma_f16(tacc, pl_smem_desc(aH + ko), pl_smem_desc(bH + ko), idesc1, acc);
+          pl_umma_f16(tacc, pl_smem_desc(aH + ko), pl_smem_desc(bL + ko), idesc1, 1u);
+          if (p.has_lo) pl_umma_f16(tacc, pl_smem_desc(aL + ko), pl_smem_desc(bH + ko), idesc1, 1u);
           if (N2) {
             const uint32_t off = (uint32_t)N1 * 128u;         // weight rows N1.. : 1024-byte aligned (N1 % 8 == 0)
-            pl_umma_f16(tmem_base + N1, pl_smem_desc(aH + ko), pl_smem_desc(bH + off + ko), idesc2, acc);
-            pl_umma_f16(tmem_base + N1, pl_smem_desc(aH + ko), pl_smem_desc(bL + off + ko), idesc2, 1u);
-            if (p.has_lo) pl_umma_f16(tmem_base + N1, pl_smem_desc(aL + ko), pl_smem_desc(bH + off + ko), idesc2, 1u);
+            pl_umma_f16(tacc + N1, pl_smem_desc(aH + ko), pl_smem_desc(bH + off + ko), idesc2, acc);
+            pl_umma_f16(tacc + N1, pl_smem_desc(aH + ko), pl_smem_desc(bL + off + ko), idesc2, 1u);
+            if (p.has_lo) pl_umma_f16(tacc + N1, pl_smem_desc(aL + ko), pl_smem_desc(bH + off + ko), idesc2, 1u);
           }
         }
         pl_umma_commit(&empty[s]);                            // the stage may be refilled once these MMAs have read it
       }
-      pl_umma_commit(&acc_full);
+      pl_umma_commit(&acc_full[buf]);
+      }
     }
   } else {
     // =============================== EPILOGUE (4 warps, TMEM lane = row = point) ===================
     const int q = warp & 3;                                   // warps 2,3,4,5 -> TMEM lane quarters 2,3,0,1
     const int r = q * 32 + lane;
-    const long long row = (long long)row0 + r;
+    for (int i = 0; i < ntile; ++i) {
+    const int buf = i % NBUF;
+    const long long row = (long long)(tile0 + i) * PL_ROWS + r;
     const bool ok = row < p.M;
-    pl_mbar_wait(&acc_full, 0u);
+    pl_mbar_wait(&acc_full[buf], (unsigned)((i / NBUF) & 1));
     pl_tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BUFC);
     const int b = ok ? (int)(row / p.n) : 0;
     const int j = ok ? (int)(row - (long long)b * p.n) : 0;
     if (p.mode != SPC_PM_VOTE) {
@@ -342,6 +367,8 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
     pl_tc_fence_before();
+    pl_mbar_arrive(&acc_empty[buf]);
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -391,7 +418,7 @@ using namespace spc;
 extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, const void *W_hi, const void *W_lo,
                              const float *bias, int N, int mode, int points_per_scene, void *Y_hi, void *Y_lo,
                              float *out, const float *seed_cm, const float *seed_xyz, float *vote_xyz,
-                             int n_tile, void *stream_) {
+                             int n_tile, int tiles_per_cta, void *stream_) {
   // rows are K * 2 bytes apart and TMA needs 16-byte strides; K need not be a multiple of the 64-element chunk
   SPC_CHECK_ARG(M >= 0 && K >= 8 && K % 8 == 0 && K <= 4096, "pm_linear: K=%d must be a multiple of 8", K);
   SPC_CHECK_ARG(N >= 1 && N <= 272, "pm_linear: N=%d out of range (1..272)", N);
@@ -414,6 +441,8 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
   // loads X once and holds an SM for less time in total, which is what a saturated pipeline wants); the vote tail
   // needs whole rows for its L2 norm and takes all of N
   SPC_CHECK_ARG(n_tile >= 0 && n_tile % 16 == 0, "pm_linear: n_tile=%d must be 0 or a multiple of 16", n_tile);
+  SPC_CHECK_ARG(tiles_per_cta >= 0 && tiles_per_cta <= 1024, "pm_linear: tiles_per_cta=%d out of range", tiles_per_cta);
+  p.tiles_per_cta = tiles_per_cta > 0 ? tiles_per_cta : 1;
   const int slice = n_tile > 0 ? n_tile : 128;
   p.NT = (mode == SPC_PM_VOTE || N <= slice) ? N : slice;
   const int n_tiles = (N + p.NT - 1) / p.NT;
@@ -437,7 +466,7 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
   if ((rc = make_map(&tB_lo, W_lo, N, K, BR)) != SPC_OK) return rc;
   const size_t smem = (size_t)stages * stage_bytes + 1024;
   SPC_CUDA(cudaFuncSetAttribute(pm_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pm_linear_kernel<<<dim3(ceil_div(M, PL_ROWS), n_tiles), PL_THREADS, smem, (cudaStream_t)stream_>>>(tA_hi, tA_lo, tB_hi,
+  pm_linear_kernel<<<dim3(ceil_div(ceil_div(M, PL_ROWS), p.tiles_per_cta), n_tiles), PL_THREADS, smem, (cudaStream_t)stream_>>>(tA_hi, tA_lo, tB_hi,
                                                                                                       tB_lo, p);
   SPC_LAUNCH_CHECK("pm_linear_kernel");
   return SPC_OK;

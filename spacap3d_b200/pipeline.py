@@ -20,7 +20,7 @@ class GraphedDetector:
     returns the slot index.  Outputs of a slot stay valid until that slot is submitted again."""
 
     def __init__(self, model, example, n_streams=2, result_keys=None, warmup=3, sa_min_tiles=16, fps_algo=None,
-                 pm_n_tile=256):
+                 pm_n_tile=256, pm_tiles_per_cta=4):
         assert example.is_cuda
         # Launch hints baked into the captured graphs (per call and thread-local: nothing process-wide changes).
         # With several batches in flight what limits throughput is how much of the GPU the latency-bound sampler
@@ -32,7 +32,8 @@ class GraphedDetector:
         if fps_algo is None:
             n = example.shape[1]
             fps_algo = _ext.FPS_BUCKET if _ext.FPS_BUCKET_MIN_N <= n <= _ext.FPS_BUCKET_MAX_N else _ext.FPS_AUTO
-        self._options = dict(sa_min_tiles=int(sa_min_tiles), fps_algo=int(fps_algo), pm_n_tile=int(pm_n_tile))
+        self._options = dict(sa_min_tiles=int(sa_min_tiles), fps_algo=int(fps_algo), pm_n_tile=int(pm_n_tile),
+                             pm_tiles_per_cta=int(pm_tiles_per_cta))
         self.model = model
         self.device = example.device
         self.n = int(n_streams)

@@ -91,19 +91,36 @@ def test_argument_checks():
                        _ext.PM_HIDDEN, 256)          # K not a multiple of 8
 
 
-def test_n_tile_hint_does_not_change_results():
-    """The per-call launch hint (output channels per CTA) only changes the grid: 256-wide layers in one CTA per row
-    tile, in two 128-channel slices (default) or in four 64-channel slices give the same bits."""
+def test_launch_hints_do_not_change_results():
+    """The per-call launch hints only change the grid and the schedule: output channels per CTA (one CTA per row tile,
+    two 128-channel slices = default, four 64-channel slices) and row tiles per CTA (1 = default; more: the CTA loops
+    with a double-buffered accumulator) give the same bits -- also with a ragged last tile and in the vote tail,
+    whose 272-column accumulator is single-buffered."""
     from spacap3d_b200 import _ext
-    M = 384
+    M = 128 * 5 + 7                                               # six row tiles, the last one ragged
     X, W, b, _ = _layer(M, 256, 256, 21, True)
-    outs = []
-    for nt in (0, 64, 256):
-        with _ext.launch_options(pm_n_tile=nt):
+    base = None
+    for nt, tpc in ((0, 0), (64, 0), (256, 0), (0, 2), (256, 4), (256, 16), (128, 5)):
+        with _ext.launch_options(pm_n_tile=nt, pm_tiles_per_cta=tpc):
             y_hi, y_lo = _ext.pm_linear(X, W, b, _ext.PM_HIDDEN, M)
-        outs.append((y_hi.clone(), y_lo.clone()))
-    for y_hi, y_lo in outs[1:]:
-        assert torch.equal(y_hi, outs[0][0]) and torch.equal(y_lo, outs[0][1])
+            out, _ = _ext.pm_linear(X, W, b, _ext.PM_OUT_CM, M)
+        got = (y_hi.clone(), y_lo.clone(), out.clone())
+        if base is None:
+            base = got
+        assert all(torch.equal(a, c) for a, c in zip(got, base)), (nt, tpc)
+    B, n, D = 2, 640, 256
+    Xv, Wv, bv, _ = _layer(B * n, D, 3 + D, 4, True)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    seed_xyz = torch.randn(B, n, 3, generator=g).to(DEV)
+    seed_cm = torch.relu(torch.randn(B, D, n, generator=g)).to(DEV)
+    ref = None
+    for tpc in (0, 3):
+        with _ext.launch_options(pm_tiles_per_cta=tpc):
+            vote_xyz, out, (hi, lo) = _ext.pm_linear(Xv, Wv, bv, _ext.PM_VOTE, n, seed_cm=seed_cm, seed_xyz=seed_xyz)
+        got = (vote_xyz.clone(), out.clone(), hi.clone(), lo.clone())
+        if ref is None:
+            ref = got
+        assert all(torch.equal(a, c) for a, c in zip(got, ref)), tpc
     with pytest.raises(RuntimeError):
         with _ext.launch_options(pm_n_tile=100):                  # not a multiple of 16
             _ext.pm_linear(X, W, b, _ext.PM_HIDDEN, M)
