@@ -109,8 +109,11 @@ def ncu_traffic(tag, source):
     try:
         with open(path) as f:
             d = json.load(f)
-        with open(os.path.join(ROOT, "spacap3d_b200", "csrc", source), "rb") as f:
-            sha = hashlib.sha256(f.read()).hexdigest()
+        h = hashlib.sha256()
+        for src in source.split(","):                      # the kernels of one op may live in several files
+            with open(os.path.join(ROOT, "spacap3d_b200", "csrc", src), "rb") as f:
+                h.update(f.read())
+        sha = h.hexdigest()
         if d.get("source_sha256") != sha:
             return None, "profiles/r2_%s_traffic.json is stale (csrc/%s changed since the capture)" % (tag, source)
         return int(d["dram_bytes_per_launch_avg"]), ("profiles/r2_%s_traffic.json (ncu --set full, dram read+write per "
@@ -632,7 +635,7 @@ def run_ours(args):
         tensor_bound = avg_flops / (tf_peak * 1e12) > avg_bytes / (hbm_peak * 1e9)
         if tensor_bound:
             achieved = avg_flops / (avg_ms * 1e-3) / 1e12
-        traffic, traffic_src = ncu_traffic("sa_fused", "sa_fused.cu")
+        traffic, traffic_src = ncu_traffic("sa_fused", "sa_common.cuh,sa_fused.cu,sa_inline.cu")
         roofline = {"kernel": name.replace("spc_", "").replace("_ex", ""), "bound": "tensor" if tensor_bound else "hbm",
                     "achieved": round(achieved, 2),
                     "peak": tf_peak if tensor_bound else hbm_peak,

@@ -53,7 +53,7 @@ def main():
         if lines:
             open(os.path.join(P, "r2_bench", os.path.basename(f)), "w").write(lines[-1] + "\n")
     for name in ("r2_ops_vs_reference_graph.json", "r2_sanitizer_racecheck.log", "r2_sanitizer_memcheck.log",
-                 "r2_train_step_profile.txt"):
+                 "r2_train_step_profile.txt", "r2_sa_layers.json", "r2_marginal_cost_config2.json"):
         if os.path.exists(os.path.join(G, name)):
             shutil.copy(os.path.join(G, name), os.path.join(P, name))
     # ncu launch list of the bench command
@@ -77,14 +77,15 @@ def main():
         open(os.path.join(P, "r2_forward_table.csv"), "w").write("\n".join(l[:170] for l in out.splitlines()) + "\n")
     tr = os.path.join(G, "r2_sa_traffic.csv")
     if os.path.exists(tr):
-        print(run([py, os.path.join(ROOT, "tools", "make_traffic_json.py"), tr, "sa_fused_pipe_kernel", "sa_fused",
-                   "sa_fused.cu", "5"]).strip())
+        print(run([py, os.path.join(ROOT, "tools", "make_traffic_json.py"), tr, "sa_fused_pipe_kernel|sa_inline_kernel", "sa_fused",
+                   "sa_common.cuh,sa_fused.cu,sa_inline.cu", "5"]).strip())
     # per-kernel ncu summaries
     out = ["# ncu --set full --clock-control none --import-source on, ONE launch per kernel (tools/profile_kernels.sh), B200.",
            "# group_points: the config-4 shape (B=8, C=132, 40 000 -> 2048 x 64; 727 MB algorithmic).  bqg_query: SA1 ball "
            "query (8 x 40 000, 2048 centres).",
            "# fps_*: 8 scenes x 40 000 -> 2048.  pm_linear: one FP / voting layer of the detector forward.  sa_fused_sa1 / "
-           "_sa2: the SA1 (64,64,128; nsample 64) and SA2 (128,128,256; nsample 32) layers.",
+           "_sa2: the SA1 (sa_inline_kernel: 64,64,128; nsample 64) and SA2 (sa_fused_pipe_kernel: 128,128,256; nsample 32) layers; "
+           "group_grad_gather: the large-cloud backward of grouping at the config-4 shape.",
            "# three_interpolate: the FP2 shape.  Per-launch times are cold-cache and serialised."]
     met = {}
     for f in sorted(glob.glob(os.path.join(G, "r2_*.raw.csv"))):

@@ -3,7 +3,8 @@
 --default-options` -> profiles/r2_<tag>_traffic.json: DRAM read+write bytes per launch of the kernels matching a
 regex, averaged over the LAST forward, together with the sha256 of the kernel source (bench.py reports the figure only
 while that hash still matches).
-    python tools/make_traffic_json.py gpurun_out/sa_traffic.csv sa_fused_pipe_kernel sa_fused sa_fused.cu 5"""
+    python tools/make_traffic_json.py gpurun_out/sa_traffic.csv "sa_fused_pipe_kernel|sa_inline_kernel" sa_fused \
+        sa_common.cuh,sa_fused.cu,sa_inline.cu 5"""
 import csv
 import hashlib
 import json
@@ -27,7 +28,10 @@ def main():
             d[r[im]] = float(r[iv].replace(",", "")) * scale[r[iu]]
     ids = sorted(per)[-per_forward:]
     tot = [per[i].get("dram__bytes_read.sum", 0) + per[i].get("dram__bytes_write.sum", 0) for i in ids]
-    sha = hashlib.sha256(open(os.path.join(ROOT, "spacap3d_b200", "csrc", source), "rb").read()).hexdigest()
+    h = hashlib.sha256()
+    for src in source.split(","):                          # comma-separated: the kernels of one op may live in several files
+        h.update(open(os.path.join(ROOT, "spacap3d_b200", "csrc", src), "rb").read())
+    sha = h.hexdigest()
     out = {"kernel": regex, "launches": len(ids), "dram_bytes_per_launch": [int(t) for t in tot],
            "dram_bytes_per_launch_avg": int(sum(tot) / max(len(tot), 1)), "source": "csrc/" + source,
            "source_sha256": sha,

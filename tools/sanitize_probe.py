@@ -3,7 +3,9 @@
     compute-sanitizer --tool racecheck python tools/sanitize_probe.py
     compute-sanitizer --tool memcheck  python tools/sanitize_probe.py
 Covers fps_cluster_kernel (DSMEM st.async + mbarrier exchange), fps_bucket_kernel (named barriers, per-warp queues),
-fps_morton_sort_kernel, sa_fused_pipe_kernel (mbarrier pipeline, tcgen05 / TMEM), pm_linear_kernel (TMA + tcgen05),
+fps_morton_sort_kernel, sa_inline_kernel / sa_fused_pipe_kernel (mbarrier pipelines, tcgen05 / TMEM), pm_linear_kernel
+(TMA + tcgen05, also looping over tiles with the double-buffered accumulator), group_points_grad (list build with atomic
+cursors + point-owned gather),
 group_points_kernel (bulk TMA staging), three_interpolate_kernel, bqg_* (grid ball query).  Sizes are small because the
 tools slow execution down ~100x; every result is also checked against the CPU oracle."""
 import os
@@ -50,5 +52,12 @@ W = _ext.split_half(torch.randn(64, 128, device=dev) / 11.0)
 hi, lo = _ext.pm_linear(X, W, torch.zeros(64, device=dev), _ext.PM_HIDDEN, 256)
 ref = torch.relu((X[0].double() + X[1].double()) @ (W[0].double() + W[1].double()).t())
 assert ((hi.double() + lo.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+with _ext.launch_options(pm_n_tile=64, pm_tiles_per_cta=2):          # two row tiles per CTA: accumulator ring
+    hi2, lo2 = _ext.pm_linear(X, W, torch.zeros(64, device=dev), _ext.PM_HIDDEN, 256)
+assert torch.equal(hi, hi2) and torch.equal(lo, lo2)
+g = torch.randn(2, 12, 96, 16, device=dev)                          # N = 9000 > 8192: the large-cloud backward
+gg = _ext.group_points_grad(g, bq, 9000)
+want_gg = oracle.group_points_grad(g.cpu().numpy(), bq.cpu().numpy(), 9000)
+assert np.allclose(gg.cpu().numpy(), want_gg, rtol=1e-5, atol=1e-5)
 torch.cuda.synchronize()
 print("sanitize probe OK")
