@@ -115,8 +115,9 @@ def main():
                 "warp instructions per scene: cluster %.3g, bucketed %.3g" % (ic / 8, ib / 8),
                 "sampling alone, CUDA-graph calls round-robin on 32 streams (tools/time_fps.py): cluster 18.4 k scenes/s, "
                 "bucketed 56.6 k scenes/s",
-                "detector pipeline (bench.py, config 2, 100 steps): 12.9 k scenes/s (round 1) -> 18.7 k scenes/s; with the SA1 "
-                "sampler replaced by a copy: 30.3 k (the sampler's cost is additive: 141 of 407 us per 8-scene batch)",
+                "detector pipeline (bench.py, config 2, 100 steps): 12.9 k scenes/s (round 1) -> 18.7 k scenes/s with this sampler "
+                "(-> 20.5 k after round 2b's fused-SA / pm_linear changes); its marginal cost in the pipeline is 161-168 us of a "
+                "389-412 us step (tools/marginal_cost.py) = the 8 CTAs x 2.95 ms it holds",
                 "top stalls of the bucketed kernel: the per-round named barrier (39 %% of all stall samples sit right behind it: "
                 "warps wait for the one with the most bucket visits), fixed-latency dependencies (wait), shared-memory "
                 "latency (short scoreboard); issue slots %s %% busy." % b["smsp__issue_active.avg.pct_of_peak_sustained_active"][0][:5]]
