@@ -680,7 +680,8 @@ static int launch_group_grad_csr(const float *grad_out, const int *offsets, cons
 }
 
 // ----------------------------------------------------------------------------------------------
-// Large clouds (N > 8192: the input level of the detector, e.g. C = 132 multiview features over 40 k points).
+// group_points backward (reference group_points_gpu.cu:43-75: one atomicAdd per element), large clouds
+// (N > 8192: the input level of the detector, e.g. C = 132 multiview features over 40 k points).
 // Staging position partitions does not pay here: a partition of <= 24 576 positions touches a small, different
 // subset of the N points, so every (channel, partition) CTA walked all N offsets for a few thousand hits and
 // combined its partial sums with global atomics (2.45 ms for 727 MB at C = 132, 4.5 % of HBM, round 1).
