@@ -28,7 +28,8 @@ def counting(name, *a):
 
 _lib.call = counting
 # --default-options: the single-call launch configuration (what bench.py's eager pass and its `roofline` block time)
-opts = {} if "--default-options" in sys.argv else dict(fps_algo=_ext.FPS_BUCKET, sa_min_tiles=16)
+opts = {} if "--default-options" in sys.argv else dict(fps_algo=_ext.FPS_BUCKET, sa_min_tiles=16, pm_n_tile=256,
+                                                         pm_tiles_per_cta=4)     # = GraphedDetector's defaults
 with torch.no_grad(), _ext.launch_options(**opts):
     for i in range(4):
         if i == 3:
