@@ -19,6 +19,9 @@ LAYERS = {
     "sa1_9ch_late_features": (4096, 9, 256, 0.2, 64, [9, 64, 64, 128]),       # in-line: 3 K steps, feature 8 read late
     "sa1_13ch_max_inline": (4096, 13, 256, 0.2, 32, [13, 64, 64, 128]),       # in-line: 4 K steps, the most it takes
     "sa1_14ch_projected": (4096, 14, 256, 0.2, 64, [14, 64, 64, 128]),        # one more channel: projected form
+    "inline_wide": (4096, 4, 256, 0.3, 32, [4, 128, 128, 256]),               # in-line form at the wide widths (one CTA/SM, D2 ring)
+    "inline_wide_ns16": (2048, 2, 128, 0.4, 16, [2, 128, 128, 128]),
+    "sa1_ns16": (4096, 1, 256, 0.2, 16, [1, 64, 64, 128]),                    # 8 centres per tile: two 16-byte stores per lane
     "sa1_multiview": (4096, 132, 256, 0.3, 64, [132, 64, 64, 128]),
     "sa2": (2048, 128, 1024, 0.4, 32, [128, 128, 128, 256]),
     "sa3": (1024, 256, 512, 0.8, 16, [256, 128, 128, 256]),
