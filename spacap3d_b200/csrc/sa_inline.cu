@@ -3,20 +3,21 @@
 // three [1x1 conv + folded BN + ReLU] + max-pool over nsample in one warp-specialised kernel with ALL THREE convs on
 // tcgen05 tensor cores.
 //
-// Round-1/2a evaluated layer 0 (3+Cf -> C1) with FFMAs in the gather stage: 256-512 FMAs and 8 x 16-byte stores per
-// (centre, neighbour) row, a third of all warp instructions of the SA1 launch (ncu source view), on a pipeline that
-// is instruction-issue bound.  Here the gather stage only writes the ROW OF INPUTS and layer 0 becomes one more
-// K = 16..64 UMMA.  To keep layer 0 at fp32 accuracy (it sees differences of nearby coordinates), inputs and weights
-// are split in fp16 (hi, lo) pairs and three products are accumulated in fp32 by the tensor core:
+// Rounds 1-2a evaluated layer 0 (3+Cf -> C1) with FFMAs in the gather stage: 256-512 FMAs and 8 x 16-byte stores per
+// (centre, neighbour) row, a third of all warp instructions of the SA1 launch (ncu source view).  Here the gather
+// stage only writes the ROW OF INPUTS and layer 0 becomes one more K = 16..64 UMMA.  To keep layer 0 at fp32 accuracy
+// (it sees differences of nearby coordinates), inputs and weights are split in fp16 (hi, lo) pairs and three products
+// are accumulated in fp32 by the tensor core:
 //     a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo            (the dropped a_lo.w_lo term is 2^-22 relative)
-// K layout, one 16-element K step per group of four inputs e = 4g .. 4g+3 (NV = 3 + Cf inputs, zero beyond NV):
+// K layout: one 16-element K step per group of four inputs e = 4g .. 4g+3 (NV = 3 + Cf inputs, zero beyond NV),
 //   A0 row  : [ hi0 lo0 hi1 lo1 hi2 lo2 hi3 lo3 | hi0 hi1 hi2 hi3 s s 0 0 ]      s = 1 in group 0, else 0
 //   W0' row : [ wh0 wh0 wh1 wh1 wh2 wh2 wh3 wh3 | wl0 wl1 wl2 wl3 bh bl 0 0 ]    (bias in group 0 only)
-// every slot position is a compile-time constant, so a gather thread packs a K step in registers and writes it with
+// Every slot position is a compile-time constant, so a gather thread packs a K step in registers and writes it with
 // two conflict-free 16-byte stores (a first version wrote 2-byte elements at run-time positions: 4-way bank conflicts,
-// a third of the kernel's shared-memory store wavefronts),
-// so the folded bias rides along and the layer-0 epilogue is TMEM -> relu -> fp16 -> H1 with no arithmetic.
-// Four groups = 16 inputs (Cf <= 13) fit the 64-element swizzle atom.
+// a third of the kernel's shared-memory store wavefronts).  The folded bias rides along on the two constant ones, so
+// the layer-0 epilogue is TMEM -> relu -> fp16 -> H1 with no arithmetic.  Four groups = 16 inputs (Cf <= 13) fit the
+// 64-element swizzle atom.  What the kernel is bound by now (L1 data pipe, then the TMEM read rate of the epilogues):
+// profiles/r2_sa_fused_limits.md.
 //
 // Pipeline per 128-row tile k (a row = one (centre, neighbour) pair; all hand-offs are mbarriers):
 //   warps 0-3   GATHER      idx, xyz, centre, features -> A0[k & 1]                       (thread = row)
@@ -27,8 +28,8 @@
 //   warps 8-11  EPILOGUE 1  D1 + b1 -> relu -> fp16 -> H2
 //   warps 12-15 EPILOGUE 2  D2 -> max over the nsample columns of a centre, + b2, relu -> out (thread = channel)
 // Every stage works on a different tile at any time, so single-buffered H1 / H2 / D0 / D1 are enough (the UMMAs
-// take ~0.1 us, the epilogues ~1 us); A0 is double-buffered so that the gather runs a tile ahead of MMA0 without
-// holding a tile of loads in registers.  TMEM: D0 (C1) + D1 (C2) + D2 (128 per block) columns; the SA1 widths
+// take ~0.1 us, the epilogues ~1 us); A0 is double-buffered and the gather issues a tile's loads one iteration before
+// it consumes them.  TMEM: D0 (C1) + D1 (C2) + D2 (128 per block) columns; the SA1 widths
 // (64, 64, 128) need 256 columns and 97 KB of shared memory, so two CTAs share an SM.
 #include "sa_common.cuh"
 
