@@ -126,6 +126,7 @@ struct PmLinearParams {
   int has_lo;                  // X comes as a hi + lo pair
   int stages;
   int tiles_per_cta;           // row tiles one CTA works through (>= 1); the accumulator is double-buffered when it fits
+  int resident;                // the CTA's whole weight slice stays in shared memory (loaded with its first tile)
   int mode;
   int n;                       // points per scene (channel-major outputs)
   const float *bias;           // (N)
@@ -164,8 +165,16 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   const int N1 = Nr > 256 ? 256 : Nr, N2 = Nr - N1;    // UMMA N of the main part and of the remainder (0 or 16)
   const int A_BYTES = PL_ROWS * 128;
   const int B_BYTES = Nr * 128;
-  const int STAGE_BYTES = A_BYTES * (1 + p.has_lo) + 2 * B_BYTES;
+  // A pipeline stage holds one K chunk of X (hi [+ lo]) and, unless the weights are RESIDENT, the matching chunk of the
+  // weight slice (hi + lo).  Resident (chosen by the host when a CTA works through several row tiles and the whole
+  // slice fits next to >= 2 stages of X): the K chunks of W are loaded once, with the first tile, into their own
+  // region in front of the stages, and every later tile only streams X -- half the bytes per tile for the 128-wide
+  // layers, which are bound by what one SM can pull out of L2.
+  const int A_STAGE = A_BYTES * (1 + p.has_lo);
+  const int W_CHUNK = 2 * B_BYTES;
+  const int STAGE_BYTES = p.resident ? A_STAGE : A_STAGE + W_CHUNK;
   const int KCH = (p.K + PL_KC - 1) / PL_KC;           // a partial last chunk is zero-filled by TMA (both operands)
+  uint8_t *stage0 = smem + (p.resident ? (size_t)KCH * W_CHUNK : 0);
   // A CTA works through up to tiles_per_cta consecutive row tiles of its channel slice.  With more than one the
   // accumulator is double-buffered in TMEM (2 x 128 or 2 x 256 columns; the 272-wide vote tail has one buffer), so
   // the epilogue of tile i overlaps the loads and MMAs of tile i + 1, and the setup (barriers, TMEM allocation, bias)
@@ -198,14 +207,17 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int c = 0; c < KCH; ++c, ++g) {                  // g: chunk counter over all tiles (the stage ring goes on)
           const int s = g % p.stages;
           if (g >= p.stages) pl_mbar_wait(&empty[s], (unsigned)((g / p.stages - 1) & 1));
-          uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-          pl_mbar_expect_tx(&full[s], (unsigned)STAGE_BYTES);
+          uint8_t *st = stage0 + (size_t)s * STAGE_BYTES;
+          const bool load_w = !p.resident || i == 0;
+          pl_mbar_expect_tx(&full[s], (unsigned)(A_STAGE + (load_w ? W_CHUNK : 0)));
           pl_tma_load(st, &tmA_hi, c * PL_KC, row0, &full[s]);
-          uint8_t *b = st + A_BYTES;
-          if (p.has_lo) { pl_tma_load(b, &tmA_lo, c * PL_KC, row0, &full[s]); b += A_BYTES; }
-          for (int r = 0; r < Nr; r += BR) {
-            pl_tma_load(b + (size_t)r * 128, &tmB_hi, c * PL_KC, n_off + r, &full[s]);
-            pl_tma_load(b + B_BYTES + (size_t)r * 128, &tmB_lo, c * PL_KC, n_off + r, &full[s]);
+          if (p.has_lo) pl_tma_load(st + A_BYTES, &tmA_lo, c * PL_KC, row0, &full[s]);
+          if (load_w) {
+            uint8_t *b = p.resident ? smem + (size_t)c * W_CHUNK : st + A_STAGE;
+            for (int r = 0; r < Nr; r += BR) {
+              pl_tma_load(b + (size_t)r * 128, &tmB_hi, c * PL_KC, n_off + r, &full[s]);
+              pl_tma_load(b + B_BYTES + (size_t)r * 128, &tmB_lo, c * PL_KC, n_off + r, &full[s]);
+            }
           }
         }
       }
@@ -225,9 +237,9 @@ pm_linear_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int s = g % p.stages;
         pl_mbar_wait(&full[s], (unsigned)((g / p.stages) & 1));
         pl_tc_fence_after();
-        const uint32_t aH = pl_s2u(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t aH = pl_s2u(stage0 + (size_t)s * STAGE_BYTES);
         const uint32_t aL = aH + A_BYTES;
-        const uint32_t bH = aH + A_BYTES * (1 + p.has_lo);
+        const uint32_t bH = p.resident ? pl_s2u(smem + (size_t)c * W_CHUNK) : aH + A_STAGE;
         const uint32_t bL = bH + B_BYTES;
 #pragma unroll
         for (int kk = 0; kk < PL_KC / 16; ++kk) {
@@ -451,10 +463,17 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
   p.mode = mode; p.n = points_per_scene; p.bias = bias;
   p.Y_hi = (__half *)Y_hi; p.Y_lo = (__half *)Y_lo; p.out = out;
   p.seed_cm = seed_cm; p.seed_xyz = seed_xyz; p.vote_xyz = vote_xyz;
-  const int stage_bytes = PL_ROWS * 128 * (1 + p.has_lo) + 2 * Nr * 128;
-  int stages = (220 * 1024) / stage_bytes;
+  const int kch = (K + PL_KC - 1) / PL_KC;
+  const int a_stage = PL_ROWS * 128 * (1 + p.has_lo), w_chunk = 2 * Nr * 128;
+  const int budget = 220 * 1024;
+  const int row_tiles = ceil_div(M, PL_ROWS);
+  const int tiles_here = p.tiles_per_cta < row_tiles ? p.tiles_per_cta : row_tiles;
+  p.resident = tiles_here > 1 && (long long)kch * w_chunk + 2LL * a_stage <= budget;
+  const int stage_bytes = p.resident ? a_stage : a_stage + w_chunk;
+  const int fixed_bytes = p.resident ? kch * w_chunk : 0;
+  int stages = (budget - fixed_bytes) / stage_bytes;
   if (stages > PL_MAX_STAGES) stages = PL_MAX_STAGES;
-  if (stages > (K + PL_KC - 1) / PL_KC) stages = (K + PL_KC - 1) / PL_KC;
+  if (stages > kch * tiles_here) stages = kch * tiles_here;    // the stage ring runs on across a CTA's tiles
   SPC_CHECK_ARG(stages >= 1, "pm_linear: a pipeline stage of %d bytes does not fit in shared memory", stage_bytes);
   p.stages = stages;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
@@ -464,7 +483,7 @@ extern "C" int spc_pm_linear(const void *X_hi, const void *X_lo, int M, int K, c
   const int BR = Nr > 256 ? Nr / 2 : Nr;
   if ((rc = make_map(&tB_hi, W_hi, N, K, BR)) != SPC_OK) return rc;
   if ((rc = make_map(&tB_lo, W_lo, N, K, BR)) != SPC_OK) return rc;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = (size_t)fixed_bytes + (size_t)stages * stage_bytes + 1024;
   SPC_CUDA(cudaFuncSetAttribute(pm_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pm_linear_kernel<<<dim3(ceil_div(ceil_div(M, PL_ROWS), p.tiles_per_cta), n_tiles), PL_THREADS, smem, (cudaStream_t)stream_>>>(tA_hi, tA_lo, tB_hi,
                                                                                                       tB_lo, p);

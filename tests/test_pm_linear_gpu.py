@@ -100,7 +100,7 @@ def test_launch_hints_do_not_change_results():
     M = 128 * 5 + 7                                               # six row tiles, the last one ragged
     X, W, b, _ = _layer(M, 256, 256, 21, True)
     base = None
-    for nt, tpc in ((0, 0), (64, 0), (256, 0), (0, 2), (256, 4), (256, 16), (128, 5)):
+    for nt, tpc in ((0, 0), (64, 0), (256, 0), (0, 2), (256, 4), (256, 16), (128, 5), (64, 3)):   # (0,2) (128,5) (64,3): W resident
         with _ext.launch_options(pm_n_tile=nt, pm_tiles_per_cta=tpc):
             y_hi, y_lo = _ext.pm_linear(X, W, b, _ext.PM_HIDDEN, M)
             out, _ = _ext.pm_linear(X, W, b, _ext.PM_OUT_CM, M)
