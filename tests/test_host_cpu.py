@@ -31,6 +31,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.spc_abi_version() == _lib.ABI_VERSION
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/spacap3d_ops.h against the ctypes argument list the Python stub binds: same number
+    of parameters, pointers where the header has pointers, int / float / size_t where it has scalars (a launch hint
+    added on one side only would silently shift every later argument)."""
+    import ctypes
+    from spacap3d_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "spacap3d_ops.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = dict(re.findall(r"\b(spc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    checked = 0
+    for name, argtypes in _lib.SIGNATURES.items():
+        params = [a.strip() for a in protos[name].replace("\n", " ").split(",")]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for prm, ct in zip(params, argtypes):
+            if "*" in prm:
+                assert ct is ctypes.c_void_p, (name, prm, ct)
+            elif prm.startswith("size_t"):
+                assert ct is ctypes.c_size_t, (name, prm, ct)
+            elif prm.startswith("float"):
+                assert ct is ctypes.c_float, (name, prm, ct)
+            elif prm.startswith(("int ", "unsigned")):
+                assert ct in (ctypes.c_int, ctypes.c_uint), (name, prm, ct)
+            elif prm.startswith(("uint64_t", "unsigned long long")):
+                assert ct is ctypes.c_uint64, (name, prm, ct)
+            elif prm.startswith("double"):
+                assert ct is ctypes.c_double, (name, prm, ct)
+            else:
+                raise AssertionError("unhandled parameter %r of %s" % (prm, name))
+            checked += 1
+    assert checked > 300
+
+
 def test_library_is_sm100a_and_uses_cluster_and_bulk_copy():
     out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "spacap3d_b200", "libspacap3d_ops.so")],
                          capture_output=True, text=True).stdout
